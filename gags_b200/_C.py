@@ -1,0 +1,101 @@
+"""ctypes binding of include/gags_b200.h.  There is no fallback: if the shared library is missing
+the import of this module raises, and every op that needs a GPU raises when CUDA is absent."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgags_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -m gags_b200.build` "
+        "(gags_b200 has no CPU or PyTorch fallback path)")
+
+lib = C.CDLL(LIB_PATH)
+
+GAGS_F_LOG_SCALES = 1
+GAGS_F_LOGIT_OPACITY = 2
+
+
+class Camera(C.Structure):
+    _fields_ = [("viewmat", C.c_float * 16), ("viewmat_dev", C.c_void_p), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("eps2d", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float),
+                ("radius_clip", C.c_float), ("scaling_modifier", C.c_float), ("flags", C.c_int32)]
+
+
+_p = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f = C.c_float
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/gags_b200.h declares
+SIGNATURES = {
+    "gags_version": (C.c_char_p, []),
+    "gags_build_arch": (C.c_char_p, []),
+    "gags_error_string": (C.c_char_p, [C.c_int]),
+    "gags_project_fwd": (C.c_int, [_p, _p, _p, _p, _i64, C.POINTER(Camera), _i32, _i32, _p, _p, _p,
+                                   _p, _p, _p, _p, _p]),
+    "gags_project_bwd": (C.c_int, [_p, _p, _p, _i64, C.POINTER(Camera), _p, _p, _p, _p, _p, _p, _p,
+                                   _p, _p]),
+    "gags_opacity_bwd": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "gags_sh_fwd": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _i64, _p, _i32, _p]),
+    "gags_sh_bwd": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _i64, _p, _i32, _p, _p, _p]),
+    "gags_tile_count": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
+    "gags_tile_scan_workspace_bytes": (_sz, [_i64]),
+    "gags_tile_scan": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
+    "gags_tile_emit": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
+    "gags_sort_pairs_workspace_bytes": (_sz, [_i64]),
+    "gags_sort_pairs": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _sz, C.POINTER(_i32), _p]),
+    "gags_tile_offsets": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "gags_blend_fwd": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "gags_blend_bwd_features": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "gags_blend_bwd_full": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                                      _p, _p, _p]),
+    "gags_l1_loss_fused": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p]),
+    "gags_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i32, _i32, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int, what: str = "gags") -> None:
+    if rc != 0:
+        msg = lib.gags_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gags_b200 ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+_launches = 0
+
+
+def count_launch(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches

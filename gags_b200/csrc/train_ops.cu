@@ -1,0 +1,127 @@
+// train_ops.cu — the two elementwise passes either side of the rasteriser in the training step
+// (SURVEY.md §8f rows 1 and 2), each fused to ONE pass over its 2 GB operands.
+//   gags_l1_loss_fused : loss = sum(|m| * |render - target|) and v_render = scale * |m| * sign(r - t)
+//       replaces  l1_loss(feature_map * seg_mask, gt * seg_mask)
+//       (/root/reference/utils/loss_utils.py:20-21 called at /root/reference/train.py:162-163) and
+//       the 4 elementwise autograd kernels behind it (mul, mul, sub, abs/sign, mean).
+//       Algorithmic bytes: 8*HW*D read (+4*HW mask), 4*HW*D written.
+//   gags_adam_step     : torch.optim.Adam(lr, betas, eps) single-tensor step
+//       (/root/reference/scene/gaussian_model.py:199,208 stepped at /root/reference/train.py:222-223),
+//       optionally zeroing the gradient in the same pass (zero_grad(set_to_none) analogue for a
+//       persistent gradient buffer).  Algorithmic bytes: 16 read + 12 (+4) written per element.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+l1_loss_kernel(const float4 *__restrict__ r, const float4 *__restrict__ t,
+               const float *__restrict__ mask, long long n4, int d4, float scale,
+               float *__restrict__ loss, float4 *__restrict__ vout) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_nc4(r + i), b = ldg_nc4(t + i);
+    const float m = mask ? fabsf(__ldg(mask + i / d4)) : 1.f;
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    acc += m * (fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw));
+    const float s = scale * m;
+    float4 g;
+    g.x = dx > 0.f ? s : (dx < 0.f ? -s : 0.f);
+    g.y = dy > 0.f ? s : (dy < 0.f ? -s : 0.f);
+    g.z = dz > 0.f ? s : (dz < 0.f ? -s : 0.f);
+    g.w = dw > 0.f ? s : (dw < 0.f ? -s : 0.f);
+    vout[i] = g;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_part[w];
+    atomicAdd(loss, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
+            float4 *__restrict__ v, long long n4, float step_size, float b1, float b2,
+            float inv_sqrt_bc2, float eps, int zero_grad) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 gi = g[i];
+    float4 mi = m[i], vi = v[i], pi = p[i];
+#define GAGS_ADAM1(c)                                             \
+    mi.c = b1 * mi.c + (1.f - b1) * gi.c;                         \
+    vi.c = b2 * vi.c + (1.f - b2) * gi.c * gi.c;                  \
+    pi.c -= step_size * (mi.c / (sqrtf(vi.c) * inv_sqrt_bc2 + eps));
+    GAGS_ADAM1(x) GAGS_ADAM1(y) GAGS_ADAM1(z) GAGS_ADAM1(w)
+#undef GAGS_ADAM1
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void adam_tail_kernel(float *p, float *g, float *m, float *v, long long start,
+                                 long long n, float step_size, float b1, float b2,
+                                 float inv_sqrt_bc2, float eps, int zero_grad) {
+  const long long i = start + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  m[i] = mi; v[i] = vi;
+  if (zero_grad) g[i] = 0.f;
+}
+
+}  // namespace
+
+extern "C" int gags_l1_loss_fused(const float *render, const float *target, const float *mask,
+                                  int64_t HW, int32_t D, float grad_scale, float *loss_out,
+                                  float *v_render, void *stream) {
+  if (!render || !target || !loss_out || !v_render || HW < 0 || D < 1) return GAGS_EINVAL;
+  if (D % 4 != 0) return GAGS_EINVAL;
+  if (!gags_aligned16(render) || !gags_aligned16(target) || !gags_aligned16(v_render)) return GAGS_EALIGN;
+  if (HW == 0) return 0;
+  const long long n4 = (long long)HW * (D / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;   // 16 resident 256-thread CTAs per SM, grid-stride
+  l1_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(render), reinterpret_cast<const float4 *>(target), mask, n4,
+      D / 4, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                              int64_t numel, float lr, float beta1, float beta2, float eps,
+                              int32_t step, int32_t zero_grad, void *stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || numel < 0 || step < 1) return GAGS_EINVAL;
+  if (!gags_aligned16(param) || !gags_aligned16(grad) || !gags_aligned16(exp_avg) ||
+      !gags_aligned16(exp_avg_sq))
+    return GAGS_EALIGN;
+  if (numel == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const long long n4 = numel / 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n4 > 0) {
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),
+        reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), n4, step_size,
+        beta1, beta2, inv_sqrt_bc2, eps, zero_grad);
+    GAGS_CHECK_LAUNCH();
+  }
+  if (n4 * 4 < numel) {
+    adam_tail_kernel<<<1, 32, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4 * 4, numel, step_size,
+                                       beta1, beta2, inv_sqrt_bc2, eps, zero_grad);
+    GAGS_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -1,0 +1,374 @@
+"""The operator boundary beneath render(): a B200-native stand-in for ``gsplat.rasterization`` as
+the reference calls it (/root/reference/gaussian_renderer/__init__.py:56-70), C = 1, packed=False.
+
+Every stage is a hand-written sm_100a kernel reached through the C-ABI of include/gags_b200.h
+(``gags_b200._C``).  PyTorch only owns the buffers, the stream and the autograd graph:
+
+    _Project   K1 (+K2 bwd)   means/quats/scales/opacities -> radii, means2d, depths, conics, opac
+    _SHColors  K3 (+bwd)      SH coefficients -> RGB
+    binning    K4-K6          tile count (fused in K1) -> scan -> emit -> radix sort -> offsets
+    _Blend     K7 (+K8 bwd)   one launch for any D; feature-only backward when geometry is frozen
+
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _C
+
+TILE = 16
+
+
+# ------------------------------------------------------------------------------------------------
+# camera struct
+# ------------------------------------------------------------------------------------------------
+def make_camera(viewmat: torch.Tensor, fx: float, fy: float, cx: float, cy: float, width: int,
+                height: int, eps2d: float = 0.3, near_plane: float = 0.01,
+                far_plane: float = 1e10, radius_clip: float = 0.0, scaling_modifier: float = 1.0,
+                flags: int = 0) -> Tuple[_C.Camera, torch.Tensor]:
+    """`viewmat` [4,4] world->camera.  A CUDA view matrix is read by the kernels straight from
+    device memory (no host round trip); a CPU one is copied into the struct."""
+    cam = _C.Camera()
+    keep = None
+    if viewmat.is_cuda:
+        keep = viewmat.detach().to(torch.float32).contiguous()
+        cam.viewmat_dev = keep.data_ptr()
+    else:
+        vm = viewmat.detach().to(torch.float32).contiguous().reshape(-1).tolist()
+        for i in range(16):
+            cam.viewmat[i] = vm[i]
+        cam.viewmat_dev = None
+    cam.fx, cam.fy, cam.cx, cam.cy = float(fx), float(fy), float(cx), float(cy)
+    cam.width, cam.height = int(width), int(height)
+    cam.eps2d, cam.near_plane, cam.far_plane = float(eps2d), float(near_plane), float(far_plane)
+    cam.radius_clip = float(radius_clip)
+    cam.scaling_modifier = float(scaling_modifier)
+    cam.flags = int(flags)
+    return cam, keep
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise ValueError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2
+# ------------------------------------------------------------------------------------------------
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, cam, cam_keep, tile_w, tile_h):
+        _C.require_cuda(means, quats, scales, opacities)
+        means, quats, scales = _f32c(means), _f32c(quats), _f32c(scales)
+        opacities = _f32c(opacities).reshape(-1)
+        N = means.shape[0]
+        if means.shape != (N, 3) or quats.shape != (N, 4) or scales.shape != (N, 3) \
+                or opacities.shape != (N,):
+            raise ValueError("means [N,3], quats [N,4], scales [N,3], opacities [N] expected")
+        dev = means.device
+        radii = torch.empty(N, dtype=torch.int32, device=dev)
+        means2d = torch.empty(N, 2, dtype=torch.float32, device=dev)
+        depths = torch.empty(N, dtype=torch.float32, device=dev)
+        conics = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        opac = torch.empty(N, dtype=torch.float32, device=dev)
+        tiles = torch.empty(N, dtype=torch.int32, device=dev)
+        geom = torch.empty(N, 8, dtype=torch.float32, device=dev)
+        _C.check(_C.lib.gags_project_fwd(_C.ptr(means), _C.ptr(quats), _C.ptr(scales),
+                                         _C.ptr(opacities), N, ctypes.byref(cam), tile_w, tile_h,
+                                         _C.ptr(radii), _C.ptr(means2d), _C.ptr(depths),
+                                         _C.ptr(conics), _C.ptr(opac), _C.ptr(tiles), _C.ptr(geom),
+                                         _C.stream_ptr()), "gags_project_fwd")
+        _C.count_launch()
+        ctx.cam, ctx.cam_keep = cam, cam_keep
+        ctx.save_for_backward(means, quats, scales, radii, conics, opac)
+        ctx.mark_non_differentiable(radii, tiles, geom)
+        return radii, means2d, depths, conics, opac, tiles, geom
+
+    @staticmethod
+    def backward(ctx, _vr, v_means2d, v_depths, v_conics, v_opac, _vt, _vg):
+        means, quats, scales, radii, conics, opac = ctx.saved_tensors
+        N = means.shape[0]
+        dev = means.device
+        need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        v_means = v_quats = v_scales = v_logit = None
+        if need_geo:
+            z2 = v_means2d.contiguous() if v_means2d is not None else torch.zeros(N, 2, device=dev)
+            z3 = v_conics.contiguous() if v_conics is not None else torch.zeros(N, 3, device=dev)
+            zd = v_depths.contiguous() if v_depths is not None else None
+            v_means = torch.empty(N, 3, device=dev)
+            v_quats = torch.empty(N, 4, device=dev)
+            v_scales = torch.empty(N, 3, device=dev)
+            _C.check(_C.lib.gags_project_bwd(_C.ptr(means), _C.ptr(quats), _C.ptr(scales), N,
+                                             ctypes.byref(ctx.cam), _C.ptr(radii), _C.ptr(conics),
+                                             _C.ptr(z2), _C.ptr(zd), _C.ptr(z3), _C.ptr(v_means),
+                                             _C.ptr(v_quats), _C.ptr(v_scales), _C.stream_ptr()),
+                     "gags_project_bwd")
+            _C.count_launch()
+        if ctx.needs_input_grad[3] and v_opac is not None:
+            if ctx.cam.flags & _C.GAGS_F_LOGIT_OPACITY:
+                v_logit = torch.empty(N, device=dev)
+                _C.check(_C.lib.gags_opacity_bwd(_C.ptr(opac), _C.ptr(v_opac.contiguous()), N,
+                                                 _C.ptr(v_logit), _C.stream_ptr()),
+                         "gags_opacity_bwd")
+                _C.count_launch()
+            else:
+                v_logit = v_opac
+        return v_means, v_quats, v_scales, v_logit, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------
+class _SHColors(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree, means, campos, coeffs, radii):
+        _C.require_cuda(means, coeffs, campos)
+        means, coeffs = _f32c(means), _f32c(coeffs)
+        N, K = coeffs.shape[0], coeffs.shape[1]
+        if coeffs.shape[2] != 3 or K < (degree + 1) ** 2:
+            raise ValueError("SH coefficients must be [N, K>=(deg+1)^2, 3]")
+        colors = torch.empty(N, 3, dtype=torch.float32, device=means.device)
+        campos = _f32c(campos)
+        _C.check(_C.lib.gags_sh_fwd(degree, _C.ptr(means), _C.ptr(campos), _C.ptr(coeffs), K,
+                                    _C.ptr(radii), N, _C.ptr(colors), 3, _C.stream_ptr()),
+                 "gags_sh_fwd")
+        _C.count_launch()
+        ctx.degree = degree
+        ctx.save_for_backward(means, campos, coeffs, radii)
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, coeffs, radii = ctx.saved_tensors
+        N, K = coeffs.shape[0], coeffs.shape[1]
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.zeros_like(means) if ctx.needs_input_grad[1] else None
+        _C.check(_C.lib.gags_sh_bwd(ctx.degree, _C.ptr(means), _C.ptr(campos), _C.ptr(coeffs), K,
+                                    _C.ptr(radii), N, _C.ptr(v_colors.contiguous()), 3,
+                                    _C.ptr(v_coeffs), _C.ptr(v_means), _C.stream_ptr()),
+                 "gags_sh_bwd")
+        _C.count_launch()
+        return None, v_means, None, v_coeffs, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K4-K6 binning (integer stage, no autograd)
+# ------------------------------------------------------------------------------------------------
+def tile_bits(n_tiles: int) -> int:
+    return int(math.floor(math.log2(n_tiles))) + 1
+
+
+@torch.no_grad()
+def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int) -> Dict:
+    """tiles_touched -> scan -> emit -> stable radix sort -> offsets.  One host sync (n_isects)."""
+    N = radii.shape[0]
+    dev = radii.device
+    st = _C.stream_ptr()
+    cum = torch.empty(N, dtype=torch.int32, device=dev)
+    n_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = _C.lib.gags_tile_scan_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _C.check(_C.lib.gags_tile_scan(_C.ptr(tiles_touched), N, _C.ptr(cum), _C.ptr(n_dev),
+                                   _C.ptr(ws), ws_bytes, st), "gags_tile_scan")
+    _C.count_launch(2)
+    n = int(n_dev.item())                     # the one host sync of the pipeline
+    n_tiles = tile_w * tile_h
+    keys_a = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    keys_b = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    vals_a = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    vals_b = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty(n_tiles + 1, dtype=torch.int32, device=dev)
+    if n > 0:
+        _C.check(_C.lib.gags_tile_emit(_C.ptr(means2d), _C.ptr(radii), _C.ptr(depths), _C.ptr(cum),
+                                       N, tile_w, tile_h, _C.ptr(keys_a), _C.ptr(vals_a), st),
+                 "gags_tile_emit")
+        sws_bytes = _C.lib.gags_sort_pairs_workspace_bytes(n)
+        sws = torch.empty(sws_bytes, dtype=torch.uint8, device=dev)
+        sel = ctypes.c_int32(0)
+        _C.check(_C.lib.gags_sort_pairs(_C.ptr(keys_a), _C.ptr(keys_b), _C.ptr(vals_a),
+                                        _C.ptr(vals_b), n, 32 + tile_bits(n_tiles), _C.ptr(sws),
+                                        sws_bytes, ctypes.byref(sel), st), "gags_sort_pairs")
+        _C.count_launch(8)
+        if sel.value == 1:
+            keys_a, vals_a = keys_b, vals_b
+    _C.check(_C.lib.gags_tile_offsets(_C.ptr(keys_a), n, n_tiles, _C.ptr(offsets), st),
+             "gags_tile_offsets")
+    _C.count_launch()
+    return dict(n_isects=n, isect_ids=keys_a[:n], flatten_ids=vals_a[:n], offsets=offsets,
+                cum_tiles=cum)
+
+
+# ------------------------------------------------------------------------------------------------
+# K7 / K8
+# ------------------------------------------------------------------------------------------------
+class _Blend(torch.autograd.Function):
+    """means2d / conics / opac are the differentiable handles of the projection outputs; the
+    kernels read the same values from the packed `geom` record."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, opac, colors, background, geom, offsets, flatten_ids,
+                width, height):
+        _C.require_cuda(colors, geom)
+        colors = _f32c(colors)
+        N, D = colors.shape
+        dev = colors.device
+        if D > 32 and D % 4 != 0:
+            raise ValueError("wide blend needs D % 4 == 0 (rasterization() pads for you)")
+        bg = _f32c(background) if background is not None else None
+        render = torch.empty(height, width, D, dtype=torch.float32, device=dev)
+        alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
+        last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
+        _C.check(_C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height,
+                                       _C.ptr(offsets), _C.ptr(flatten_ids), _C.ptr(render),
+                                       _C.ptr(alphas), _C.ptr(last_ids), _C.stream_ptr()),
+                 "gags_blend_fwd")
+        _C.count_launch((D + 255) // 256 if D > 32 else 1)
+        ctx.dims = (width, height, D, N)
+        ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
+        ctx.mark_non_differentiable(last_ids)
+        return render, alphas, last_ids
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas, _vl):
+        colors, bg, geom, offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
+        width, height, D, N = ctx.dims
+        dev = colors.device
+        need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        need_col = ctx.needs_input_grad[3]
+        if v_render is None:
+            v_render = torch.zeros(height, width, D, device=dev)
+        v_render = _f32c(v_render)
+        st = _C.stream_ptr()
+        v_colors = torch.zeros(N, D, device=dev) if need_col else None
+        v_m = v_c = v_o = v_bg = None
+        if not need_geo:
+            if need_col:
+                # frozen geometry: the feature-only fast path
+                _C.check(_C.lib.gags_blend_bwd_features(_C.ptr(geom), D, width, height,
+                                                        _C.ptr(offsets), _C.ptr(flatten_ids),
+                                                        _C.ptr(v_render), _C.ptr(v_colors), st),
+                         "gags_blend_bwd_features")
+                _C.count_launch((D + 255) // 256 if D > 32 else 1)
+        else:
+            v_m = torch.zeros(N, 2, device=dev)
+            v_c = torch.zeros(N, 3, device=dev)
+            v_o = torch.zeros(N, device=dev)
+            va = _f32c(v_alphas) if v_alphas is not None else None
+            _C.check(_C.lib.gags_blend_bwd_full(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width,
+                                                height, _C.ptr(offsets), _C.ptr(flatten_ids),
+                                                _C.ptr(alphas), _C.ptr(last_ids), _C.ptr(v_render),
+                                                _C.ptr(va), _C.ptr(v_m), _C.ptr(v_c), _C.ptr(v_o),
+                                                _C.ptr(v_colors), st), "gags_blend_bwd_full")
+            _C.count_launch(2)
+        if ctx.needs_input_grad[4] and bg is not None:
+            v_bg = (v_render * (1.0 - alphas)[..., None]).sum(dim=(0, 1))
+        return v_m, v_c, v_o, v_colors, v_bg, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# public operator
+# ------------------------------------------------------------------------------------------------
+def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx, cy, width: int,
+                   height: int, background=None, sh_degree: Optional[int] = None,
+                   render_mode: str = "RGB", eps2d: float = 0.3, near_plane: float = 0.01,
+                   far_plane: float = 1e10, radius_clip: float = 0.0,
+                   scaling_modifier: float = 1.0, flags: int = 0):
+    """One view.  `flags` selects the fused activations (raw log-scales / logit opacities).
+    Returns render [H,W,D'], alphas [H,W], info."""
+    if render_mode not in ("RGB", "D", "ED", "RGB+D", "RGB+ED"):
+        raise ValueError(f"unknown render_mode {render_mode}")
+    tile_w = (width + TILE - 1) // TILE
+    tile_h = (height + TILE - 1) // TILE
+    if 32 + tile_bits(tile_w * tile_h) > 64:
+        raise ValueError("image too large for the 64-bit intersection key")
+    cam, keep = make_camera(viewmat, fx, fy, cx, cy, width, height, eps2d, near_plane, far_plane,
+                            radius_clip, scaling_modifier, flags)
+    radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
+        means, quats, scales, opacities, cam, keep, tile_w, tile_h)
+    binned = bin_and_sort(means2d.detach(), radii, depths.detach(), tiles, tile_w, tile_h)
+    if sh_degree is None:
+        cols = colors
+        if cols.dim() != 2 or cols.shape[0] != means.shape[0]:
+            raise ValueError("colors must be [N, D] when sh_degree is None")
+    else:
+        vm = viewmat.detach().to(torch.float32)
+        campos = torch.linalg.inv(vm)[:3, 3].contiguous().to(means.device)
+        cols = _SHColors.apply(int(sh_degree), means, campos, colors, radii)
+    bg = background
+    if render_mode in ("RGB+D", "RGB+ED"):
+        cols = torch.cat([cols, depths[:, None]], dim=-1)
+        if bg is not None:
+            bg = torch.cat([bg, torch.zeros(1, device=bg.device, dtype=bg.dtype)])
+    elif render_mode in ("D", "ED"):
+        cols = depths[:, None]
+        bg = None
+    D = cols.shape[1]
+    pad = (-D) % 4 if D > 32 else 0
+    if pad:
+        cols = torch.nn.functional.pad(cols, (0, pad))
+        if bg is not None:
+            bg = torch.nn.functional.pad(bg, (0, pad))
+    # the [1,N,2] handle is what render() hands out as "viewspace_points"; blending through its
+    # [0] view makes .retain_grad() on it behave as in the reference (:75-78)
+    means2d_c = means2d.unsqueeze(0)
+    render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
+                                            binned["offsets"], binned["flatten_ids"], width, height)
+    if pad:
+        render = render[..., :D]
+    if render_mode in ("ED", "RGB+ED"):
+        render = torch.cat([render[..., :-1],
+                            render[..., -1:] / alphas.clamp(min=1e-10)[..., None]], dim=-1)
+    info = dict(radii=radii, means2d=means2d_c, depths=depths, conics=conics, opacities=opac,
+                tile_width=tile_w, tile_height=tile_h, tiles_per_gauss=tiles,
+                isect_ids=binned["isect_ids"], flatten_ids=binned["flatten_ids"],
+                isect_offsets=binned["offsets"][:-1].reshape(tile_h, tile_w),
+                n_isects=binned["n_isects"], last_ids=last_ids, width=width, height=height,
+                tile_size=TILE, n_cameras=1, geom=geom)
+    return render, alphas, info
+
+
+def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width: int, height: int,
+                  near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0,
+                  eps2d: float = 0.3, sh_degree: Optional[int] = None, packed: bool = False,
+                  tile_size: int = 16, backgrounds=None, render_mode: str = "RGB", **unused):
+    """Same call shape as the reference's use of gsplat.rasterization
+    (/root/reference/gaussian_renderer/__init__.py:56-70): activated inputs, viewmats [C,4,4],
+    Ks [C,3,3], backgrounds [C,D]; returns (colors [C,H,W,D'], alphas [C,H,W,1], info) with
+    info["radii"] [C,N] and info["means2d"] [C,N,2] — the two keys GAGS reads (:74,:76,:83)."""
+    if tile_size != TILE:
+        raise ValueError("tile_size must be 16")
+    if packed:
+        raise ValueError("packed=True is not supported (the reference passes packed=False)")
+    if viewmats.dim() != 3 or Ks.dim() != 3 or viewmats.shape[0] != Ks.shape[0]:
+        raise ValueError("viewmats [C,4,4] and Ks [C,3,3] expected")
+    C = viewmats.shape[0]
+    Kh = Ks.detach().cpu().tolist()
+    outs, alps, infos = [], [], []
+    for c in range(C):
+        bg = backgrounds[c] if backgrounds is not None else None
+        r, a, info = rasterize_view(means, quats, scales, opacities, colors, viewmats[c],
+                                    Kh[c][0][0], Kh[c][1][1], Kh[c][0][2], Kh[c][1][2], width,
+                                    height, bg, sh_degree, render_mode, eps2d, near_plane,
+                                    far_plane, radius_clip)
+        outs.append(r)
+        alps.append(a[..., None])
+        infos.append(info)
+    info = dict(infos[0])
+    if C == 1:
+        # keep means2d as a differentiable view so that .retain_grad() works as in the reference
+        info["radii"] = infos[0]["radii"][None]
+        info["means2d"] = infos[0]["means2d"]
+        info["depths"] = infos[0]["depths"][None]
+        info["conics"] = infos[0]["conics"][None]
+    else:
+        for k in ("radii", "depths", "conics"):
+            info[k] = torch.stack([i[k] for i in infos])
+        info["means2d"] = torch.cat([i["means2d"] for i in infos])
+    info["n_cameras"] = C
+    return torch.stack(outs), torch.stack(alps), info

@@ -1,0 +1,57 @@
+"""Losses that consume the render and seed the backward, named as in
+/root/reference/utils/loss_utils.py:20-30, plus the fused single-pass L1."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import _C
+
+
+def l1_loss(network_output, gt):
+    return torch.abs(network_output - gt).mean()
+
+
+def l1_loss_map(network_output, gt):
+    return torch.abs(network_output - gt).mean(dim=0)
+
+
+def l2_loss(network_output, gt):
+    return ((network_output - gt) ** 2).mean()
+
+
+def cos_loss(network_output, gt):
+    return 1 - F.cosine_similarity(network_output, gt, dim=0).mean()
+
+
+class _L1Fused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, render_hwd, target_hwd, mask_hw):
+        _C.require_cuda(render_hwd, target_hwd)
+        if render_hwd.shape != target_hwd.shape or render_hwd.dim() != 3:
+            raise ValueError("render and target must both be [H,W,D]")
+        r = render_hwd.contiguous()
+        t = target_hwd.contiguous()
+        H, W, D = r.shape
+        m = mask_hw.contiguous().reshape(-1) if mask_hw is not None else None
+        loss = torch.zeros(1, dtype=torch.float32, device=r.device)
+        v = torch.empty_like(r)
+        numel = float(H * W * D)
+        _C.check(_C.lib.gags_l1_loss_fused(_C.ptr(r), _C.ptr(t), _C.ptr(m), H * W, D, 1.0 / numel,
+                                           _C.ptr(loss), _C.ptr(v), _C.stream_ptr()),
+                 "gags_l1_loss_fused")
+        _C.count_launch()
+        ctx.save_for_backward(v)
+        return loss[0] / numel
+
+    @staticmethod
+    def backward(ctx, g):
+        (v,) = ctx.saved_tensors
+        return v * g, None, None
+
+
+def l1_loss_fused(render_dhw, gt_hwd, mask_hw=None):
+    """mean(|render*mask - gt*mask|) (train.py:162-163) in ONE pass that also produces the gradient.
+    `render_dhw` is render()["render"] ([D,H,W] view of the channel-last raster); `gt_hwd` is the
+    target in channel-last layout [H,W,D]; `mask_hw` an optional non-negative [H,W] mask."""
+    return _L1Fused.apply(render_dhw.permute(1, 2, 0), gt_hwd, mask_hw)

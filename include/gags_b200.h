@@ -1,0 +1,181 @@
+/* gags_b200.h — C-ABI of the B200-native GAGS feature rasteriser.
+ *
+ * Drop-in boundary.  The reference reaches all of this arithmetic through one
+ * Python call, gsplat.rasterization(...), at /root/reference/gaussian_renderer/__init__.py:56-70
+ * (gsplat is an external pip dependency, /root/reference/environment.yml:26).  Each entry point
+ * below replaces one CUDA op that call dispatches to; the op it replaces is named in the comment.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *   - the caller allocates and owns every buffer (incl. workspaces); nothing is retained;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync inside
+ *     unless stated;
+ *   - return 0 on success, a positive cudaError_t, or a negative GAGS_E* code; never throws;
+ *   - float = IEEE fp32, row-major, densely packed unless a stride is given.
+ */
+#ifndef GAGS_B200_H
+#define GAGS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAGS_TILE 16
+
+#define GAGS_EINVAL  (-1)   /* bad argument (null pointer, bad size, unsupported D)        */
+#define GAGS_EALIGN  (-2)   /* pointer/stride not aligned as required (16 B for rows)       */
+#define GAGS_ESMALL  (-3)   /* workspace too small                                         */
+#define GAGS_ERANGE  (-4)   /* value out of supported range (e.g. tile_bits + 32 > 64)      */
+
+/* flags for gags_camera_t.flags */
+#define GAGS_F_LOG_SCALES      1  /* scales are log-scales: apply exp() then * scaling_modifier
+                                     (GaussianModel.get_scaling, scene/gaussian_model.py:116-118) */
+#define GAGS_F_LOGIT_OPACITY   2  /* opacities are logits: apply sigmoid()
+                                     (GaussianModel.get_opacity, scene/gaussian_model.py:133-134) */
+
+/* Host struct describing one pinhole view: what render() derives from a Camera at
+ * gaussian_renderer/__init__.py:27-38 (K from FoV) and :55 (viewmat = world_view_transform^T). */
+typedef struct gags_camera {
+  float viewmat[16];       /* row-major 4x4 world -> camera (host copy)                  */
+  const float *viewmat_dev;/* optional DEVICE pointer to the same 16 floats; when non-NULL the
+                              kernels read it instead of viewmat[] (no host round trip)    */
+  float fx, fy, cx, cy;    /* intrinsics in pixels                                       */
+  int32_t width, height;   /* image size in pixels                                       */
+  float eps2d;             /* 0.3  : added to the 2-D covariance diagonal                */
+  float near_plane;        /* 0.01                                                      */
+  float far_plane;         /* 1e10                                                      */
+  float radius_clip;       /* 0                                                         */
+  float scaling_modifier;  /* render(..., scaling_modifier) :42                           */
+  int32_t flags;           /* GAGS_F_*                                                   */
+} gags_camera_t;
+
+/* library / build identification (static strings) */
+const char *gags_version(void);
+const char *gags_build_arch(void);           /* "sm_100a" */
+const char *gags_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  projection + frustum cull  (replaces gsplat fully_fused_projection_fwd)
+ * In : means[N,3] quats[N,4] (w,x,y,z; normalised in-kernel) scales[N,3] opacities[N]
+ * Out: radii[N] (0 = culled) means2d[N,2] depths[N] conics[N,3]
+ *      opac_out[N]      activated opacity (may be NULL)
+ *      tiles_touched[N] number of 16x16 tiles overlapped = pass 1 of isect_tiles (may be NULL)
+ *      geom[N,8]        packed blend record {mx,my,a,b,c,opacity,depth,radius} (may be NULL)
+ * tile_w/tile_h are only used for tiles_touched.
+ */
+int gags_project_fwd(const float *means, const float *quats, const float *scales,
+                     const float *opacities, int64_t N, const gags_camera_t *cam /*host*/,
+                     int32_t tile_w, int32_t tile_h, int32_t *radii, float *means2d,
+                     float *depths, float *conics, float *opac_out, int32_t *tiles_touched,
+                     float *geom, void *stream);
+
+/* K2  VJP of K1 (replaces fully_fused_projection_bwd; App. A.7), chained through the fused
+ * activations selected by cam->flags.  Gradient outputs may be NULL individually.
+ * In : forward inputs + radii + conics, v_means2d[N,2] v_depths[N] (NULL = 0) v_conics[N,3]
+ * Out: v_means[N,3] v_quats[N,4] v_scales[N,3]   (w.r.t. the RAW inputs given to the forward) */
+int gags_project_bwd(const float *means, const float *quats, const float *scales, int64_t N,
+                     const gags_camera_t *cam /*host*/, const int32_t *radii,
+                     const float *conics, const float *v_means2d, const float *v_depths,
+                     const float *v_conics, float *v_means, float *v_quats, float *v_scales,
+                     void *stream);
+
+/* sigmoid VJP for the fused opacity activation: v_logit = v_opac * o * (1 - o). */
+int gags_opacity_bwd(const float *opac_act, const float *v_opac, int64_t N, float *v_logit,
+                     void *stream);
+
+/* K3  spherical harmonics -> RGB (replaces gsplat spherical_harmonics fwd; App. A.2; basis ==
+ * /root/reference/utils/sh_utils.py:57-112).  colors = max(SH(dir) + 0.5, 0) for radii > 0.
+ * In : means[N,3], campos[3] (DEVICE), coeffs[N,K,3] (K >= (deg+1)^2), radii[N] (NULL = all)
+ * Out: colors[N, out_stride] first 3 entries of each row written (out_stride >= 3)           */
+int gags_sh_fwd(int32_t degree, const float *means, const float *campos /*device*/,
+                const float *coeffs, int32_t K, const int32_t *radii, int64_t N, float *colors,
+                int32_t out_stride, void *stream);
+
+/* K3 bwd: v_coeffs[N,K,3] (rows of culled Gaussians and bases above `degree` are zeroed),
+ * v_means[N,3] (+= gradient through the view direction; may be NULL).                         */
+int gags_sh_bwd(int32_t degree, const float *means, const float *campos /*device*/,
+                const float *coeffs, int32_t K, const int32_t *radii, int64_t N,
+                const float *v_colors, int32_t v_stride, float *v_coeffs, float *v_means,
+                void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  tile intersection (replaces gsplat isect_tiles; App. A.3) — integer stage, exact.
+ * gags_tile_count : tiles_touched[N] from (means2d, radii)            (pass 1)
+ * gags_tile_scan  : cum_tiles[N] = inclusive prefix sum (int32), *n_isects_dev = total
+ * gags_tile_emit  : isect_ids[n] = (tile << 32) | depth_bits, flatten_ids[n] = gaussian index,
+ *                   emitted in ascending Gaussian index, row-major tiles   (pass 2)
+ */
+int gags_tile_count(const float *means2d, const int32_t *radii, int64_t N, int32_t tile_w,
+                    int32_t tile_h, int32_t *tiles_touched, void *stream);
+size_t gags_tile_scan_workspace_bytes(int64_t N);
+int gags_tile_scan(const int32_t *tiles_touched, int64_t N, int32_t *cum_tiles,
+                   int32_t *n_isects_dev, void *workspace, size_t workspace_bytes, void *stream);
+int gags_tile_emit(const float *means2d, const int32_t *radii, const float *depths,
+                   const int32_t *cum_tiles, int64_t N, int32_t tile_w, int32_t tile_h,
+                   int64_t *isect_ids, int32_t *flatten_ids, void *stream);
+
+/* K5  stable LSD radix sort of (int64 key, int32 value) on bits [0, end_bit)
+ * (replaces gsplat's cub::DeviceRadixSort::SortPairs call).  Ping-pong buffers: the result is in
+ * (keys_a, vals_a) if *selector_host == 0 else (keys_b, vals_b).                              */
+size_t gags_sort_pairs_workspace_bytes(int64_t n);
+int gags_sort_pairs(int64_t *keys_a, int64_t *keys_b, int32_t *vals_a, int32_t *vals_b, int64_t n,
+                    int32_t end_bit, void *workspace, size_t workspace_bytes,
+                    int32_t *selector_host /*host*/, void *stream);
+
+/* K6  tile offsets (replaces gsplat isect_offset_encode; App. A.4).
+ * offsets[n_tiles + 1]: offsets[t] = first sorted index with tile >= t; offsets[n_tiles] = n.  */
+int gags_tile_offsets(const int64_t *isect_ids_sorted, int64_t n, int32_t n_tiles,
+                      int32_t *offsets, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7  alpha-blend forward (replaces gsplat rasterize_to_pixels_fwd and the channel_chunk loop
+ * + torch.cat around it; App. A.5).  One launch for any D (D % 4 == 0, rows 16-B aligned).
+ * In : geom[N,8] (from gags_project_fwd), colors[N,D] (row stride = D), background[D] or NULL,
+ *      offsets[n_tiles+1], flatten_ids[n_isects]
+ * Out: render[H,W,D] alphas[H,W] last_ids[H,W] (index into flatten_ids of the last contributor)
+ */
+int gags_blend_fwd(const float *geom, const float *colors, int32_t D, const float *background,
+                   int32_t width, int32_t height, const int32_t *offsets,
+                   const int32_t *flatten_ids, float *render, float *alphas, int32_t *last_ids,
+                   void *stream);
+
+/* K8a feature-only backward (frozen geometry; the only gradient train.py consumes,
+ * /root/reference/scene/gaussian_model.py:192-206):  v_colors[g,:] += sum_px w(g,px) v_render[px,:]
+ * with w identical to the forward weight.  v_colors[N,D] must be zero-initialised by the caller. */
+int gags_blend_bwd_features(const float *geom, int32_t D, int32_t width, int32_t height,
+                            const int32_t *offsets, const int32_t *flatten_ids,
+                            const float *v_render, float *v_colors, void *stream);
+
+/* K8b full backward (replaces rasterize_to_pixels_bwd; App. A.6).  Outputs must be
+ * zero-initialised; v_colors may be NULL (skip), v_alphas may be NULL (= 0).  D <= 256.
+ * Out: v_means2d[N,2] v_conics[N,3] v_opacities[N] v_colors[N,D]                              */
+int gags_blend_bwd_full(const float *geom, const float *colors, int32_t D,
+                        const float *background, int32_t width, int32_t height,
+                        const int32_t *offsets, const int32_t *flatten_ids,
+                        const float *render_alphas, const int32_t *last_ids,
+                        const float *v_render, const float *v_alphas, float *v_means2d,
+                        float *v_conics, float *v_opacities, float *v_colors, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * §8f-1  fused distillation loss: loss = mean(|render - target| * mask) and its gradient in one
+ * pass (replaces l1_loss(feature_map*mask, gt*mask), /root/reference/utils/loss_utils.py:20-21 and
+ * train.py:162-163).  render/target/v_render are channel-last [HW, D]; mask[HW] or NULL.
+ * loss_out[1] must be zero-initialised; v_render = sign(r - t) * mask^2... see DESIGN.md.       */
+int gags_l1_loss_fused(const float *render, const float *target, const float *mask, int64_t HW,
+                       int32_t D, float grad_scale, float *loss_out, float *v_render,
+                       void *stream);
+
+/* §8f-2  fused Adam on the per-Gaussian feature table (replaces torch.optim.Adam(lr, eps=1e-15)
+ * on _semantic_feature, /root/reference/scene/gaussian_model.py:199,208; train.py:222-223).
+ * Updates param/m/v in place; if zero_grad != 0 the gradient is zeroed in the same pass.       */
+int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t numel,
+                   float lr, float beta1, float beta2, float eps, int32_t step, int32_t zero_grad,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAGS_B200_H */

@@ -1,0 +1,47 @@
+"""Shared test helpers: tiny hand-built scenes and tolerance checks."""
+import math
+
+import torch
+
+from oracle import gags_oracle as O
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| relative to the scale of the reference tensor b (1e-4 bar of north_star)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = max(float(b.abs().max()), 1e-12)
+    return float((a - b).abs().max()) / scale
+
+
+def frac_bad(a, b, rtol=1e-4):
+    """fraction of elements whose error exceeds rtol * tensor scale (threshold-flip tolerant)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = max(float(b.abs().max()), 1e-12)
+    return float(((a - b).abs() > rtol * scale).double().mean())
+
+
+def identity_cam(width, height, fov_deg=60.0):
+    fovx = math.radians(fov_deg)
+    fx = width / (2 * math.tan(fovx / 2))
+    fovy = 2 * math.atan(height / (2 * fx))
+    return fovx, fovy, torch.eye(4)
+
+
+def front_scene(n, width, height, d, seed=0, z=(3.0, 9.0), sigma_px=(1.5, 6.0), dtype=torch.float32):
+    """n Gaussians in front of an identity camera, all inside the frustum; activated params."""
+    g = torch.Generator().manual_seed(seed)
+    fovx, fovy, vm = identity_cam(width, height)
+    fx = width / (2 * math.tan(fovx / 2))
+    zz = z[0] + (z[1] - z[0]) * torch.rand(n, generator=g)
+    u = torch.rand(n, generator=g) * width
+    v = torch.rand(n, generator=g) * height
+    means = torch.stack([(u - width / 2) * zz / fx, (v - height / 2) * zz / fx, zz], -1)
+    spx = sigma_px[0] + (sigma_px[1] - sigma_px[0]) * torch.rand(n, generator=g)
+    scales = (zz * spx / fx)[:, None] * torch.exp(0.3 * torch.randn(n, 3, generator=g))
+    quats = torch.randn(n, 4, generator=g)
+    opac = torch.rand(n, generator=g) * 0.9 + 0.05
+    colors = torch.randn(n, d, generator=g)
+    K = O.intrinsics_from_fov(fovx, fovy, width, height)
+    return dict(means=means.to(dtype), quats=quats.to(dtype), scales=scales.to(dtype),
+                opacities=opac.to(dtype), colors=colors.to(dtype), viewmat=vm.to(dtype),
+                K=K.to(dtype), width=width, height=height, fovx=fovx, fovy=fovy)
