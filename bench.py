@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — views/sec of the GAGS distillation step on synthetic Gaussians (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # product arm (sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU oracle port
+  torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU, view-parallel
+
+One step = one optimiser step of the train.py loop (/root/reference/train.py:109-228) with frozen
+geometry on the config-3 shape (N=2M Gaussians, 1080x1920, D=256): for each of `views_per_step`
+views per rank  render() -> fused L1 against a fixed random target -> backward to the per-Gaussian
+features;  then (N>1) NCCL all-reduce of the feature gradient;  then Adam on the feature table.
+value = views/sec over the whole job (all ranks), inputs resident in HBM.
+e2e   = the same loop with the per-view inputs (view matrix, target segment map + embedding table)
+        copied from pinned host memory each view and the loss read back to the host each step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "views/sec fwd+bwd (N=2M Gaussians, 1080p, D=256)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gags_b200", choices=["gags_b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = headline)")
+    ap.add_argument("--views-per-step", type=int, default=None,
+                    help="views rendered per rank between optimiser steps (default 1; 4 when N>1)")
+    ap.add_argument("--n", type=int, default=None, help="override N (debug only; invalidates value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """The reference's implementation of this path (gsplat) is CUDA-only and absent; its CPU
+    stand-in is the oracle port, timed on all host cores on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from gags_b200.synthetic import CONFIGS, config_scene
+    from oracle.cpu_baseline import time_view
+    n, h, w, d = CONFIGS[args.config]
+    scene = config_scene(args.config)
+    times, info = [], None
+    for i in range(args.warmup + args.steps):
+        info = time_view(scene, scene.cameras[i % len(scene.cameras)], d, n_tiles=24, seed=i)
+        if i >= args.warmup:
+            times.append(info["seconds_per_view"])
+        if sum(times) > 150:
+            break
+    sec = sum(times) / len(times)
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": "views/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config{args.config}: N={n}, {h}x{w}, D={d}, fwd+bwd_feat, "
+                                   "CPU oracle port (gsplat itself is CUDA-only and not installed)"},
+            "cpu_baseline": {"value": 1.0 / sec, "unit": "views/s", "cores": info["cores"],
+                             "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": 1.0 / sec, "unit": "views/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=gags_b200) needs a CUDA device: there is no CPU fallback")
+    import torch.distributed as dist
+    from gags_b200 import _C, parallel, rasterization as R
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import CONFIGS, config_scene
+    from gags_b200.utils.loss_utils import l1_loss_fused
+
+    rank, world, local = parallel.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    kviews = args.views_per_step or (1 if world == 1 else 4)
+
+    n, H, W, D = CONFIGS[args.config]
+    scene = config_scene(args.config)
+    if args.n:
+        n = args.n
+        for f in ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest",
+                  "semantic_feature"):
+            setattr(scene, f, getattr(scene, f)[:n].contiguous())
+    pc = GaussianModel(3, device=dev)
+    pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                           scene.features_dc, scene.features_rest, scene.semantic_feature)
+    pc.training_setup(OptimizationParams(), fused_optimizer=True)
+    cams = [c.to(dev) for c in scene.cameras]
+    n_views = len(cams)
+    bg = torch.zeros(3, device=dev)
+
+    # Targets: a compact (segment map, embedding table) pair per target, like the reference's
+    # (seg_map, img_embed) inputs to read_sam_clip_feature (scene/dataset_readers.py:54-121).
+    n_targets, n_seg = 2, 256
+    g = torch.Generator().manual_seed(4321)
+    seg_host = [torch.randint(0, n_seg, (H // 8 + 1, W // 8 + 1), generator=g, dtype=torch.int32)
+                .repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].contiguous().pin_memory()
+                for _ in range(n_targets)]
+    emb_host = [(0.1 * torch.randn(n_seg, D, generator=g)).pin_memory() for _ in range(n_targets)]
+    vm_host = [c.world_view_transform.cpu().pin_memory() for c in cams]
+
+    def assemble_target(seg_dev, emb_dev):
+        return emb_dev[seg_dev.long()]                       # [H,W,D] gather on the device
+
+    targets_dev = [assemble_target(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
+
+    def one_view(cam, target):
+        pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
+        loss = l1_loss_fused(pkg["render"], target)
+        loss.backward()
+        return loss
+
+    def opt_step():
+        if world > 1:
+            parallel.allreduce_grads([pc._semantic_feature], world)
+        pc.optimizer.step()
+        pc.optimizer.zero_grad(set_to_none=True)
+
+    def step_resident(step):
+        loss = None
+        for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+            loss = one_view(cams[v], targets_dev[v % n_targets])
+        opt_step()
+        return loss
+
+    def step_e2e(step):
+        loss = None
+        h2d = 0
+        for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+            cam = cams[v]
+            cam.world_view_transform = vm_host[v].to(dev, non_blocking=True)
+            seg = seg_host[v % n_targets].to(dev, non_blocking=True)
+            emb = emb_host[v % n_targets].to(dev, non_blocking=True)
+            h2d += vm_host[v].numel() * 4 + seg.numel() * 4 + emb.numel() * 4
+            loss = one_view(cam, assemble_target(seg, emb))
+        opt_step()
+        return float(loss.item()), h2d                       # D2H read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = _C.launches()
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(warmup + i)
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        sampler.join()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
+        return ms, last, sampler.summary(), _C.launches() - l0
+
+    ms, _, clocks, launches = timed(step_resident, args.steps, args.warmup)
+    views_total = args.steps * kviews * world
+    value = views_total / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e, last, _, _ = timed(step_e2e, max(3, args.steps // 2), 2)
+        steps_e = max(3, args.steps // 2)
+        e2e = {"value": steps_e * kviews * world / (ms_e * 1e-3), "unit": "views/s",
+               "h2d_bytes_per_step": int(last[1]), "d2h_bytes_per_step": 4}
+
+    # ---- per-stage device times for the roofline (rank 0, single views, CUDA events) -------------
+    stage_ms, stats, roofline = {}, {}, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured" if peaks else "fallback"
+        acc = {}
+        reps = 5
+        for i in range(reps):
+            R.stage_events = []
+            cam = cams[(7 * i) % n_views]
+            pkg = render(cam, pc, None, bg)
+            R._mark("loss_start")
+            loss = l1_loss_fused(pkg["render"], targets_dev[0])
+            R._mark("loss")
+            loss.backward()
+            R._mark("backward_end")
+            pc.optimizer.step()
+            R._mark("adam")
+            pc.optimizer.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            ev = R.stage_events
+            R.stage_events = None
+            for (n0, a), (n1, b) in zip(ev[:-1], ev[1:]):
+                acc.setdefault(n1, []).append(a.elapsed_time(b))
+            if i == 0:
+                radii = pkg["radii"]
+                stats["n_visible"] = int((radii > 0).sum())
+        stage_ms = {k: sum(v) / len(v) for k, v in acc.items()}
+        nv = stats.get("n_visible", n)
+        fwd_bytes = nv * 4 * D + H * W * (4 * D + 8)
+        bwd_bytes = H * W * (4 * D + 8) + nv * 4 * D
+        kname = "blend_fwd" if stage_ms.get("blend_fwd", 0) >= stage_ms.get("blend_bwd", 0) \
+            else "blend_bwd"
+        kbytes = fwd_bytes if kname == "blend_fwd" else bwd_bytes
+        ach = kbytes / (stage_ms[kname] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "peak_kind": peak_kind,
+                    "traffic": None, "algorithmic_bytes": kbytes,
+                    "avg_launch_ms": stage_ms[kname]}
+        step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4) + H * W * (4 * D + 8) + n * (4 * D + 24)
+        stats["step_hbm_frac_of_8TBps"] = step_bytes / (ms * 1e-3 / (args.steps * kviews)) / 8e12
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import time_view
+        t0 = time.time()
+        info = time_view(scene, scene.cameras[0], D, n_tiles=32)
+        cpu = {"value": info["views_per_s"], "unit": "views/s", "cores": info["cores"],
+               "kind": "port", "sample": info["sample"],
+               "wall_s": round(time.time() - t0, 1)}
+        stats["n_isects"] = info["n_isects"]
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"config{args.config}: N={n}, {H}x{W}, D={D}, render + fused "
+                                       "L1 + feature backward + fused Adam (frozen geometry)",
+                           "views_per_step_per_gpu": kviews, "parallelism": f"view-dp{world}",
+                           "l2": "inputs (2 GB feature table, 2 GB raster) exceed the 126 MB L2",
+                           "optimizer_in_timed_region": True},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "stage_ms": stage_ms, "stats": stats}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,17 @@ from . import _C
 
 TILE = 16
 
+# Optional per-stage timing hooks (used by bench.py for the roofline numbers): when `stage_events`
+# is a list, every stage boundary appends (name, torch.cuda.Event) recorded on the current stream.
+stage_events = None
+
+
+def _mark(name: str) -> None:
+    if stage_events is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        stage_events.append((name, ev))
+
 
 # ------------------------------------------------------------------------------------------------
 # camera struct
@@ -245,7 +256,9 @@ class _Blend(torch.autograd.Function):
             v_render = torch.zeros(height, width, D, device=dev)
         v_render = _f32c(v_render)
         st = _C.stream_ptr()
+        _mark("bwd_start")
         v_colors = torch.zeros(N, D, device=dev) if need_col else None
+        _mark("bwd_zero")
         v_m = v_c = v_o = v_bg = None
         if not need_geo:
             if need_col:
@@ -266,6 +279,7 @@ class _Blend(torch.autograd.Function):
                                                 _C.ptr(va), _C.ptr(v_m), _C.ptr(v_c), _C.ptr(v_o),
                                                 _C.ptr(v_colors), st), "gags_blend_bwd_full")
             _C.count_launch(2)
+        _mark("blend_bwd")
         if ctx.needs_input_grad[4] and bg is not None:
             v_bg = (v_render * (1.0 - alphas)[..., None]).sum(dim=(0, 1))
         return v_m, v_c, v_o, v_colors, v_bg, None, None, None, None, None
@@ -289,9 +303,12 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
         raise ValueError("image too large for the 64-bit intersection key")
     cam, keep = make_camera(viewmat, fx, fy, cx, cy, width, height, eps2d, near_plane, far_plane,
                             radius_clip, scaling_modifier, flags)
+    _mark("start")
     radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
         means, quats, scales, opacities, cam, keep, tile_w, tile_h)
+    _mark("project")
     binned = bin_and_sort(means2d.detach(), radii, depths.detach(), tiles, tile_w, tile_h)
+    _mark("bin_sort")
     if sh_degree is None:
         cols = colors
         if cols.dim() != 2 or cols.shape[0] != means.shape[0]:
@@ -319,6 +336,7 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     means2d_c = means2d.unsqueeze(0)
     render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
                                             binned["offsets"], binned["flatten_ids"], width, height)
+    _mark("blend_fwd")
     if pad:
         render = render[..., :D]
     if render_mode in ("ED", "RGB+ED"):

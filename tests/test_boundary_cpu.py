@@ -1,0 +1,138 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, the host mirror keeps the reference's surface, and nothing silently falls back."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gags_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "gags_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gags_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(_C.lib, name), f"{name} declared in the header but not exported"
+        assert name in _C.SIGNATURES, f"{name} has no ctypes signature"
+    assert _C.lib.gags_build_arch() == b"sm_100a"
+    assert b"invalid" in _C.lib.gags_error_string(-1)
+
+
+def test_argument_validation_without_a_gpu():
+    """Entry points reject bad arguments before touching the device."""
+    from gags_b200 import _C
+    assert _C.lib.gags_blend_fwd(None, None, 3, None, 8, 8, None, None, None, None, None, None) == -1
+    assert _C.lib.gags_tile_count(None, None, 4, 1, 1, None, None) == -1
+    assert _C.lib.gags_adam_step(None, None, None, None, 4, 0.1, 0.9, 0.999, 1e-8, 1, 0, None) == -1
+    assert _C.lib.gags_sort_pairs_workspace_bytes(0) > 0
+
+
+def test_struct_layout_matches_header():
+    import ctypes
+    from gags_b200 import _C
+    # 16 floats + pointer + 4 floats + 2 ints + 5 floats + int = 64 + 8 + 16 + 8 + 20 + 4 = 120
+    assert ctypes.sizeof(_C.Camera) == 120
+    assert _C.Camera.viewmat_dev.offset == 64 and _C.Camera.fx.offset == 72
+
+
+def test_gaussian_model_capture_restore_roundtrip():
+    """13-tuple and 12-tuple layouts of scene/gaussian_model.py:63-113."""
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    sc = make_scene(50, 32, 32, 16, seed=1, n_views=2)
+    pc = GaussianModel(3, device="cpu")
+    pc.create_from_tensors(sc.xyz, sc.scaling, sc.rotation, sc.opacity, sc.features_dc,
+                           sc.features_rest, sc.semantic_feature)
+    opt = OptimizationParams()
+    pc.training_setup(opt)
+    assert [g["name"] for g in pc.optimizer.param_groups] == ["semantic_feature"]
+    assert pc.optimizer.param_groups[0]["lr"] == opt.semantic_feature_lr
+    assert pc.optimizer.defaults["eps"] == 1e-15
+    assert not pc._xyz.requires_grad and not pc._opacity.requires_grad
+    assert pc._semantic_feature.requires_grad
+    pc._semantic_feature.grad = torch.ones_like(pc._semantic_feature)
+    pc.optimizer.step()
+    tup = pc.capture()
+    assert len(tup) == 13 and tup[0] == pc.active_sh_degree and tup[12] is pc._semantic_feature
+    pc2 = GaussianModel(3, device="cpu")
+    pc2.create_from_tensors(sc.xyz, sc.scaling, sc.rotation, sc.opacity)
+    pc2.training_setup(opt)
+    pc2.restore(tup, opt)
+    assert torch.equal(pc2.get_semantic_feature, pc.get_semantic_feature)
+    assert torch.equal(pc2.get_xyz, pc.get_xyz)
+    # 12-tuple (RGB checkpoint): a fresh zero feature table of width 16 is created
+    pc3 = GaussianModel(3, device="cpu")
+    pc3.restore(tup[:12], opt)
+    assert pc3.get_semantic_feature.shape == (50, 16)
+    assert float(pc3.get_semantic_feature.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        pc3.restore(tup[:5], opt)
+    # getters = activations of :34-42
+    assert torch.allclose(pc.get_scaling, sc.scaling.exp())
+    assert torch.allclose(pc.get_opacity, torch.sigmoid(sc.opacity))
+    assert torch.allclose(pc.get_rotation.norm(dim=1), torch.ones(50))
+    assert pc.get_features.shape == (50, 16, 3)
+    assert pc.update_learning_rate(10) is None
+    pc.oneupSHdegree()
+    assert pc.active_sh_degree == 1
+
+
+def test_render_signature_matches_reference():
+    import inspect
+    from gags_b200.gaussian_renderer import render
+    params = list(inspect.signature(render).parameters.items())
+    names = [n for n, _ in params]
+    assert names == ["viewpoint_camera", "pc", "pipe", "bg_color", "feature_mode",
+                     "scaling_modifier", "override_color", "render_mode"]
+    d = {n: p.default for n, p in params}
+    assert d["feature_mode"] is True and d["scaling_modifier"] == 1.0
+    assert d["override_color"] is None and d["render_mode"] == "RGB"
+
+
+def test_no_cpu_fallback():
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    sc = make_scene(20, 32, 32, 4, seed=2, n_views=2)
+    pc = GaussianModel(3, device="cpu")
+    pc.create_from_tensors(sc.xyz, sc.scaling, sc.rotation, sc.opacity, sc.features_dc,
+                           sc.features_rest, sc.semantic_feature)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        render(sc.cameras[0], pc, None, torch.zeros(3))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gags_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_synthetic_scene_is_deterministic_and_shaped():
+    from gags_b200.synthetic import CONFIGS, make_scene
+    a = make_scene(100, 64, 96, 8, seed=5, n_views=4)
+    b = make_scene(100, 64, 96, 8, seed=5, n_views=4)
+    assert torch.equal(a.xyz, b.xyz) and torch.equal(a.semantic_feature, b.semantic_feature)
+    assert a.xyz.shape == (100, 3) and a.opacity.shape == (100, 1) and a.rotation.shape == (100, 4)
+    assert a.cameras[0].world_view_transform.shape == (4, 4)
+    # stored transposed: translation sits in the last ROW (scene/cameras.py:58)
+    assert float(a.cameras[0].world_view_transform[3, :3].abs().sum()) > 0
+    assert float(a.cameras[0].world_view_transform[:3, 3].abs().sum()) == 0
+    assert CONFIGS[3] == (2_000_000, 1080, 1920, 256)
+
+
+def test_loss_utils_match_reference_formulas():
+    from gags_b200.utils.loss_utils import cos_loss, l1_loss, l1_loss_map, l2_loss
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(6, 5, 4, generator=g), torch.randn(6, 5, 4, generator=g)
+    assert torch.isclose(l1_loss(a, b), (a - b).abs().mean())
+    assert l1_loss_map(a, b).shape == (5, 4)
+    assert torch.isclose(l2_loss(a, b), ((a - b) ** 2).mean())
+    assert torch.isclose(cos_loss(a, b), 1 - torch.nn.functional.cosine_similarity(a, b, 0).mean())

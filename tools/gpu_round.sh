@@ -1,0 +1,11 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, a short bench. Logs land in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+echo "pytest rc=${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+echo "bench rc=$?" >> gpurun_out/bench.err
+tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err
