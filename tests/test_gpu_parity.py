@@ -217,7 +217,9 @@ def test_sh_forward_backward_match_oracle():
         (out * v.cuda()).sum().backward()
         assert rel_err(out, ref) < 1e-5, deg
         assert rel_err(cg.grad, cr.grad) < 1e-5, deg
-        assert rel_err(mg.grad, mr.grad) < 1e-4, deg
+        # degree 0 has no view dependence: the oracle's graph never touches `means`
+        mref = mr.grad if mr.grad is not None else torch.zeros_like(mr)
+        assert rel_err(mg.grad, mref) < 1e-4, deg
 
 
 def test_projection_backward_matches_oracle_autograd():
