@@ -39,6 +39,8 @@ SIGNATURES = {
     "gags_version": (C.c_char_p, []),
     "gags_build_arch": (C.c_char_p, []),
     "gags_error_string": (C.c_char_p, [C.c_int]),
+    "gags_set_blend_impl": (C.c_int, [_i32]),
+    "gags_get_blend_impl": (C.c_int, []),
     "gags_project_fwd": (C.c_int, [_p, _p, _p, _p, _i64, C.POINTER(Camera), _i32, _i32, _p, _p, _p,
                                    _p, _p, _p, _p, _p]),
     "gags_project_bwd": (C.c_int, [_p, _p, _p, _i64, C.POINTER(Camera), _p, _p, _p, _p, _p, _p, _p,

@@ -15,3 +15,14 @@ extern "C" const char *gags_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "unknown gags error";
 }
+
+// 0 = auto (tensor-core path whenever the shape allows), 1 = SIMT kernels only, 2 = tensor-core
+// kernels required (GAGS_EINVAL when the shape does not fit).  Process-wide; used by the parity
+// tests to pin one implementation against the other.
+int g_gags_blend_impl = 0;
+extern "C" int gags_set_blend_impl(int32_t impl) {
+  if (impl < 0 || impl > 2) return GAGS_EINVAL;
+  g_gags_blend_impl = impl;
+  return 0;
+}
+extern "C" int gags_get_blend_impl(void) { return g_gags_blend_impl; }

@@ -313,6 +313,13 @@ int launch_wide(const float *geom, const float *colors, int D, int ch0, const fl
 
 }  // namespace
 
+// defined in blend_fwd_tc.cu / api.cu
+int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const float *background,
+                      int32_t width, int32_t height, const int32_t *offsets,
+                      const int32_t *flatten_ids, float *render, float *alphas, int32_t *last_ids,
+                      cudaStream_t st);
+extern int g_gags_blend_impl;
+
 extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
                               const float *background, int32_t width, int32_t height,
                               const int32_t *offsets, const int32_t *flatten_ids, float *render,
@@ -330,6 +337,10 @@ extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
   if (D % 4 != 0) return GAGS_EINVAL;
   if (!gags_aligned16(colors) || !gags_aligned16(render) || (background && !gags_aligned16(background)))
     return GAGS_EALIGN;
+  if (g_gags_blend_impl != 1 && D % 16 == 0)
+    return gags_blend_fwd_tc(geom, colors, D, background, width, height, offsets, flatten_ids,
+                             render, alphas, last_ids, st);
+  if (g_gags_blend_impl == 2) return GAGS_EINVAL;
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
     const int nj = (nch + 63) / 64;

@@ -1,0 +1,423 @@
+// blend_fwd_tc.cu — K7 alpha-blend forward for wide features on the 5th-gen tensor cores.
+// Replaces gsplat rasterize_to_pixels_fwd<CDIM> + the channel_chunk=32 loop + torch.cat around it
+// (reached from /root/reference/gaussian_renderer/__init__.py:56-70); semantics = SURVEY.md A.5.
+//
+// The D-wide blend of one 16x8 half tile is the dense product
+//        render[128 px, D] = Wt[128 px, G] * F[G, D],      Wt[p, g] = alpha_g(p) * T_g(p)
+// over the tile's depth-sorted Gaussians.  fp32 parity (1e-4) is kept on bf16 tensor cores by
+// splitting both operands x = hi + lo (bf16 each, |x - hi - lo| <= 2^-18 |x|) and issuing three
+// products hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (measured 4e-6 relative,
+// tools/umma_probe.cu).
+//
+// One CTA = one half tile, 9 warps, warp-specialised, two smem stages of 32 Gaussians:
+//   warps 4-7  producers: scan the tile list 128 entries at a time, cull every Gaussian whose
+//              alpha >= 1/255 ellipse misses the half tile (exact: such a Gaussian contributes to no
+//              pixel), append survivors (+ a 4-bit mask of the 8x4 pixel blocks it can touch) to a
+//              ring; per batch gather the survivors' feature rows with coalesced 32-B loads, split
+//              them to bf16 hi/lo in registers and store them in the MN-major SWIZZLE_128B layout.
+//   warps 0-3  one thread per pixel: evaluate alpha, run the transmittance chain, write the
+//              weight row [hi(32) | lo(32)] (128 B, K-major SWIZZLE_128B).
+//   warp 8     one thread issues tcgen05.mma (M=128, N=D, K=16) x 3 products x 2 k-steps per batch;
+//              tcgen05.commit frees the stage.
+// Epilogue: tcgen05.ld -> + T*background -> per-warp transpose in smem -> 128-B coalesced
+// streaming stores of the channel-last raster.
+//
+// Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
+// hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
+#include "umma.cuh"
+
+namespace {
+
+constexpr int KB = 32;        // Gaussians per batch (= one 128-B row of [hi|lo] bf16 weights)
+constexpr int RING = 256;     // survivor ring capacity (power of two)
+constexpr int TC_THREADS = 288;
+
+struct TcCtl {
+  uint64_t list[2], full[2], free_[2];
+  uint32_t tmem_base;
+  int gcount[2], gbase[2];
+  int skip[2];
+  int done_warps, any_mma;
+  int wcnt[4];
+  float Tfin[128];
+};
+
+template <int NATOM>
+struct TcLayout {
+  static constexpr int BPART = NATOM * 4096;           // one bf16 part (hi or lo) of one stage
+  static constexpr int A_OFF = 0;                      // 2 stages x 16 KB
+  static constexpr int B_OFF = 32768;                  // [stage][part][BPART]
+  static constexpr int RING_OFF = B_OFF + 4 * BPART;
+  static constexpr int CTL_OFF = RING_OFF + RING * 36;
+  static constexpr int BYTES = CTL_OFF + (int)sizeof(TcCtl) + 1024;   // + alignment slack
+  static constexpr int TCOLS = NATOM == 1 ? 64 : (NATOM == 2 ? 128 : 256);
+};
+
+// conservative reach of the alpha >= 1/255 ellipse; returns false when the Gaussian can never pass
+__device__ __forceinline__ bool alpha_extent(float a, float b, float c, float op, float &hx,
+                                             float &hy) {
+  const float L = __logf(255.f * op);
+  if (!(L > -1e-3f)) return false;
+  const float Lm = fmaxf(L, 0.f) + 2e-3f;
+  const float det = a * c - b * b;
+  if (det > 0.f) {
+    const float inv = 2.f * Lm / det;
+    hx = sqrtf(inv * c) * 1.0005f + 0.02f;
+    hy = sqrtf(inv * a) * 1.0005f + 0.02f;
+  } else {
+    hx = hy = 1e9f;
+  }
+  return true;
+}
+
+template <int NATOM>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, int D, int ch0,
+             int nch, const float *__restrict__ bg, int W, int H, int tile_w,
+             const int *__restrict__ offsets, const int *__restrict__ ids,
+             float *__restrict__ render, float *__restrict__ alphas, int *__restrict__ last_ids) {
+  using L = TcLayout<NATOM>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char *sA = sm + L::A_OFF;
+  unsigned char *sB = sm + L::B_OFF;
+  float4 *rg0 = reinterpret_cast<float4 *>(sm + L::RING_OFF);
+  float4 *rg1 = rg0 + RING;
+  int *rgid = reinterpret_cast<int *>(rg1 + RING);
+  TcCtl &ctl = *reinterpret_cast<TcCtl *>(sm + L::CTL_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = (blockIdx.y >> 1) * tile_w + blockIdx.x;
+  const int x0 = blockIdx.x * GAGS_TILE, y0 = blockIdx.y * 8;
+  const int s = offsets[tile], e = offsets[tile + 1];
+
+  if (tid == 0) {
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&ctl.list[k], 128);
+      mbar_init(&ctl.full[k], 256);
+      mbar_init(&ctl.free_[k], 1);
+      ctl.gcount[k] = 0; ctl.gbase[k] = 0; ctl.skip[k] = 0;
+    }
+    ctl.done_warps = 0; ctl.any_mma = 0;
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = ctl.tmem_base;
+
+  if (warp < 4) {
+    // ======================= pixel warps: one thread per pixel =====================================
+    const int pw = warp;
+    const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
+    const int pxi = x0 + dx, pyi = y0 + dy;
+    const bool inside = (pxi < W) && (pyi < H);
+    const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+    float T = 1.f;
+    int last = 0;
+    bool done = !inside, counted = false;
+    const uint32_t rowoff = (uint32_t)tid * 128u;
+    int i = 0;
+    for (;; ++i) {
+      const int st = i & 1;
+      mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
+      const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+      if (nb == 0) break;
+      const int base = *reinterpret_cast<volatile int *>(&ctl.gbase[st]);
+      if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+      unsigned char *arow = sA + st * 16384;
+      const bool wdone = __all_sync(0xffffffffu, done);
+      if (wdone) {
+        if (lane == 0) atomicAdd(&ctl.skip[st], 1);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = z;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int g = c * 8 + k;
+            w[k] = 0.f;
+            if (g < nb) {
+              const int slot = (base + g) & (RING - 1);
+              const float4 r1 = rg1[slot];
+              if ((__float_as_uint(r1.w) >> pw) & 1u) {
+                const float4 r0 = rg0[slot];
+                if (!done) {
+                  const float a = eval_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, px, py);
+                  if (a > 0.f) {
+                    const float Tn = T * (1.f - a);
+                    if (Tn <= GAGS_T_STOP) {
+                      done = true;
+                    } else {
+                      w[k] = a * T;
+                      T = Tn;
+                      last = __float_as_int(r1.z);
+                    }
+                  }
+                }
+              }
+            }
+          }
+          uint4 h, l;
+          split_pack2(w[0], w[1], h.x, l.x);
+          split_pack2(w[2], w[3], h.y, l.y);
+          split_pack2(w[4], w[5], h.z, l.z);
+          split_pack2(w[6], w[7], h.w, l.w);
+          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = h;
+          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + (c + 4) * 16)) = l;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&ctl.full[st]);
+      if (!counted && __all_sync(0xffffffffu, done)) {
+        counted = true;
+        if (lane == 0) atomicAdd(&ctl.done_warps, 1);
+      }
+    }
+    ctl.Tfin[tid] = T;
+    if (inside && ch0 == 0) {
+      const size_t pix = (size_t)pyi * W + pxi;
+      alphas[pix] = 1.f - T;
+      last_ids[pix] = last;
+    }
+    // every MMA issued has completed once the last batch's commit has arrived
+    if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
+  } else if (warp < 8) {
+    // ======================= producer warps ========================================================
+    const int p = tid - 128, pw = warp - 4;
+    const float hx0 = (float)x0 + 0.5f, hy0 = (float)y0 + 0.5f;
+    int scan = s, qtail = 0, qhead = 0;
+    for (int i = 0;; ++i) {
+      const int st = i & 1;
+      const bool stop = *reinterpret_cast<volatile int *>(&ctl.done_warps) == 4;
+      // make the stop decision uniform over the 128 producer threads
+      if (lane == 0) ctl.wcnt[pw] = stop ? 1 : 0;
+      named_bar_sync(1, 128);
+      const bool stop_all = (ctl.wcnt[0] & ctl.wcnt[1] & ctl.wcnt[2] & ctl.wcnt[3]) != 0;
+      named_bar_sync(1, 128);
+      while (!stop_all && (qtail - qhead) < KB && scan < e) {
+        const int idx = scan + p;
+        bool keep = false;
+        unsigned mask = 0;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        int gid = 0;
+        if (idx < e) {
+          gid = ids[idx];
+          a0 = geom[gid * 2];
+          a1 = geom[gid * 2 + 1];
+          float hx, hy;
+          if (alpha_extent(a0.z, a0.w, a1.x, a1.y, hx, hy)) {
+            const float lx = a0.x - hx, ux = a0.x + hx, ly = a0.y - hy, uy = a0.y + hy;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
+              if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
+            }
+            keep = mask != 0u;
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) ctl.wcnt[pw] = __popc(bal);
+        named_bar_sync(1, 128);
+        int basec = qtail, total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = ctl.wcnt[k];
+          if (k < pw) basec += c;
+          total += c;
+        }
+        if (keep) {
+          const int slot = (basec + __popc(bal & ((1u << lane) - 1u))) & (RING - 1);
+          rg0[slot] = a0;
+          rg1[slot] = make_float4(a1.x, a1.y, __int_as_float(idx), __uint_as_float(mask));
+          rgid[slot] = gid;
+        }
+        qtail += total;
+        scan += 128;
+        named_bar_sync(1, 128);
+      }
+      const int nb = stop_all ? 0 : min(KB, qtail - qhead);
+      if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+      if (p == 0) {
+        ctl.gcount[st] = nb;
+        ctl.gbase[st] = qhead & (RING - 1);
+      }
+      mbar_arrive(&ctl.list[st]);
+      if (nb == 0) break;
+      // gather + split the feature rows of this batch: warp pw owns rows [8 pw, 8 pw + 8)
+      unsigned char *bhi = sB + (st * 2 + 0) * L::BPART;
+      unsigned char *blo = sB + (st * 2 + 1) * L::BPART;
+      const int n0 = lane * 8;
+      const int nbr = (nb + 15) & ~15;               // rows the MMAs will read
+      if (n0 < nch) {
+        const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 v[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kk = pw * 8 + half * 4 + j;
+            if (kk < nb) {
+              const int gid = rgid[(qhead + kk) & (RING - 1)];
+              const float4 *src =
+                  reinterpret_cast<const float4 *>(colors + (size_t)gid * D + ch0 + n0);
+              v[j][0] = __ldg(src);
+              v[j][1] = __ldg(src + 1);
+            } else {
+              v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kk = pw * 8 + half * 4 + j;
+            if (kk < nbr) {
+              uint4 h, l;
+              split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
+              split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
+              split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
+              split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
+              const uint32_t off =
+                  (uint32_t)(kk >> 3) * 1024u + sw128((uint32_t)(kk & 7) * 128u + (coff & 127u)) +
+                  (coff & ~127u);
+              *reinterpret_cast<uint4 *>(bhi + off) = h;
+              *reinterpret_cast<uint4 *>(blo + off) = l;
+            }
+          }
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&ctl.full[st]);
+      qhead += nb;
+    }
+  } else {
+    // ======================= MMA issuer ============================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(nch, false, true);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      uint32_t acc = 0;
+      int seen[2] = {0, 0};
+      for (int i = 0;; ++i) {
+        const int st = i & 1;
+        mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
+        const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+        if (nb == 0) break;
+        mbar_wait_bounded(&ctl.full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const int votes_now = *reinterpret_cast<volatile int *>(&ctl.skip[st]);
+        const int votes = votes_now - seen[st];
+        seen[st] = votes_now;
+        if (votes < 4) {
+          const int nk = (nb + 15) >> 4;
+          for (int ks = 0; ks < nk; ++ks) {
+            const uint64_t ahi = umma_desc_sw128(a_addr + st * 16384 + ks * 32, 16, 1024);
+            const uint64_t alo = umma_desc_sw128(a_addr + st * 16384 + 64 + ks * 32, 16, 1024);
+            const uint64_t bhi =
+                umma_desc_sw128(b_addr + (st * 2 + 0) * L::BPART + ks * 2048, 4096, 1024);
+            const uint64_t blo =
+                umma_desc_sw128(b_addr + (st * 2 + 1) * L::BPART + ks * 2048, 4096, 1024);
+            umma_bf16_ss(tb, ahi, bhi, idesc, acc);
+            acc = 1;
+            umma_bf16_ss(tb, ahi, blo, idesc, 1);
+            umma_bf16_ss(tb, alo, bhi, idesc, 1);
+          }
+        }
+        umma_commit(&ctl.free_[st]);
+      }
+      ctl.any_mma = (int)acc;
+    }
+    __syncwarp();
+  }
+
+  // ========================= epilogue: TMEM -> registers -> smem transpose -> HBM ==================
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 8) {
+    const bool any = ctl.any_mma != 0;
+    const int q = warp & 3, half = warp >> 2;
+    float *stg = reinterpret_cast<float *>(sm + warp * 4096);
+    const int nchunk = (nch + 31) >> 5;
+    const float Tp = ctl.Tfin[q * 32 + lane];
+    for (int cidx = half; cidx < nchunk; cidx += 2) {
+      const int c0 = cidx * 32;
+      uint32_t r[32];
+      if (any) {
+        tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = 0u;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        float4 v = make_float4(__uint_as_float(r[cc * 4]), __uint_as_float(r[cc * 4 + 1]),
+                               __uint_as_float(r[cc * 4 + 2]), __uint_as_float(r[cc * 4 + 3]));
+        if (bg != nullptr && c0 + cc * 4 < nch) {
+          const float4 b = *reinterpret_cast<const float4 *>(bg + ch0 + c0 + cc * 4);
+          v.x = fmaf(Tp, b.x, v.x); v.y = fmaf(Tp, b.y, v.y);
+          v.z = fmaf(Tp, b.z, v.z); v.w = fmaf(Tp, b.w, v.w);
+        }
+        *reinterpret_cast<float4 *>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int ql = it * 4 + (lane >> 3), cc = lane & 7;
+        const float4 v = *reinterpret_cast<const float4 *>(stg + ql * 32 + ((cc ^ (ql & 7)) << 2));
+        const int xx = x0 + ((q & 1) << 3) + (ql & 7), yy = y0 + ((q >> 1) << 2) + (ql >> 3);
+        const int ch = c0 + cc * 4;
+        if (xx < W && yy < H && ch < nch)
+          stg_cs4(reinterpret_cast<float4 *>(render + ((size_t)yy * W + xx) * D + ch0 + ch), v);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<L::TCOLS>(tb);
+}
+
+template <int NATOM>
+int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
+              int H, const int *offsets, const int *ids, float *render, float *alphas,
+              int *last_ids, cudaStream_t st) {
+  using L = TcLayout<NATOM>;
+  const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
+  const int hh = (H + 7) / 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(blend_fwd_tc<NATOM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  blend_fwd_tc<NATOM><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
+      reinterpret_cast<const float4 *>(geom), colors, D, ch0, nch, bg, W, H, tw, offsets, ids,
+      render, alphas, last_ids);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// Tensor-core wide forward: 32 < D, D % 16 == 0.  Channels are processed 256 per launch.
+int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const float *background,
+                      int32_t width, int32_t height, const int32_t *offsets,
+                      const int32_t *flatten_ids, float *render, float *alphas, int32_t *last_ids,
+                      cudaStream_t st) {
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const int natom = (nch + 63) / 64;
+    int rc;
+    switch (natom) {
+      case 1: rc = launch_tc<1>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
+      case 2: rc = launch_tc<2>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
+      case 3: rc = launch_tc<3>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
+      default: rc = launch_tc<4>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
+    }
+    if (rc != 0) return rc;
+  }
+  return 0;
+}

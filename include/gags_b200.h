@@ -57,6 +57,11 @@ const char *gags_version(void);
 const char *gags_build_arch(void);           /* "sm_100a" */
 const char *gags_error_string(int code);
 
+/* Implementation selector for the wide (D > 32) blend kernels: 0 = auto (tcgen05 tensor-core path
+ * whenever D % 16 == 0, else SIMT), 1 = SIMT only, 2 = tensor-core required.  Process-wide. */
+int gags_set_blend_impl(int32_t impl);
+int gags_get_blend_impl(void);
+
 /* ---------------------------------------------------------------------------------------------
  * K1  projection + frustum cull  (replaces gsplat fully_fused_projection_fwd)
  * In : means[N,3] quats[N,4] (w,x,y,z; normalised in-kernel) scales[N,3] opacities[N]

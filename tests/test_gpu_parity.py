@@ -134,6 +134,45 @@ def test_blend_forward_matches_oracle(D):
     assert float((last.cpu() != ref_last).double().mean()) < 1e-3
 
 
+@pytest.fixture
+def blend_impl():
+    """Pin the wide blend implementation (0 auto, 1 SIMT, 2 tcgen05) for one test."""
+    from gags_b200 import _C
+
+    def set_impl(v):
+        _C.check(_C.lib.gags_set_blend_impl(v))
+    yield set_impl
+    _C.lib.gags_set_blend_impl(0)
+
+
+@pytest.mark.parametrize("D,n,opac_lo", [(48, 1500, 0.05), (64, 1500, 0.05), (128, 6000, 0.5),
+                                         (192, 1500, 0.05), (256, 6000, 0.5), (512, 1500, 0.05)])
+def test_tensor_core_forward_matches_simt_and_oracle(D, n, opac_lo, blend_impl):
+    """tcgen05 path (bf16 hi/lo split, 3 products) vs the fp32 SIMT kernel and the fp64 oracle.
+    The dense cases (n = 6000, opaque) run many batches per tile and terminate early."""
+    from gags_b200 import rasterization as R
+    W, H = 112, 72
+    sc = front_scene(n, W, H, D, seed=300 + D, sigma_px=(1.0, 8.0))
+    sc["opacities"] = sc["opacities"].clamp_min(opac_lo)
+    st = _stages(sc)
+    g = torch.Generator().manual_seed(1)
+    bg = torch.rand(D, generator=g)
+    m2d, con, op, offs, ids = _blend_ref(st, sc["colors"], bg, W, H)
+    ref, ref_a, ref_last = O.blend_fwd(m2d, con, sc["colors"].double(), op, bg.double(), W, H, offs, ids)
+    args = (st["means2d"], st["conics"], st["opac"], sc["colors"].cuda(), bg.cuda(), st["geom"],
+            st["offsets"], st["flatten_ids"], W, H)
+    blend_impl(1)
+    simt, a_s, l_s = R._Blend.apply(*args)
+    blend_impl(2)
+    tc, a_t, l_t = R._Blend.apply(*args)
+    torch.cuda.synchronize()
+    # same fp32 weight chain, compiled twice (fma contraction may differ by an ulp)
+    assert rel_err(a_t, a_s) < 1e-5 and float((l_s != l_t).double().mean()) < 1e-3
+    assert rel_err(tc, simt) < 3e-5
+    assert frac_bad(tc, ref, RTOL) < 1e-4 and rel_err(tc, ref) < 5e-3
+    assert float((l_t.cpu() != ref_last).double().mean()) < 1e-3
+
+
 def test_wide_blend_equals_channelwise_narrow():
     """single-pass wide-D kernel == the reference's 32-channel chunking (App. C-8)."""
     from gags_b200 import rasterization as R
