@@ -488,6 +488,12 @@ int gags_blend_bwd_geom_wide(const float *geom, const float *colors, int32_t D,
                              const float *v_render, const float *v_alphas, float *v_means2d,
                              float *v_conics, float *v_opacities, cudaStream_t st);
 
+// defined in blend_bwd_tc.cu / api.cu
+int gags_blend_bwd_features_tc(const float *geom, int32_t D, int32_t width, int32_t height,
+                               const int32_t *offsets, const int32_t *flatten_ids,
+                               const float *v_render, float *v_colors, cudaStream_t st);
+extern int g_gags_blend_impl;
+
 extern "C" int gags_blend_bwd_features(const float *geom, int32_t D, int32_t width, int32_t height,
                                        const int32_t *offsets, const int32_t *flatten_ids,
                                        const float *v_render, float *v_colors, void *stream) {
@@ -503,6 +509,10 @@ extern "C" int gags_blend_bwd_features(const float *geom, int32_t D, int32_t wid
   }
   if (D % 4 != 0) return GAGS_EINVAL;
   if (!gags_aligned16(v_render) || !gags_aligned16(v_colors)) return GAGS_EALIGN;
+  if (g_gags_blend_impl != 1 && D % 16 == 0)
+    return gags_blend_bwd_features_tc(geom, D, width, height, offsets, flatten_ids, v_render,
+                                      v_colors, st);
+  if (g_gags_blend_impl == 2) return GAGS_EINVAL;
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
     const int nj = (nch + 63) / 64;

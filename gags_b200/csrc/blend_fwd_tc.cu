@@ -39,7 +39,8 @@ struct TcCtl {
   int skip[2];
   int done_warps, any_mma;
   int wcnt[4];
-  float Tfin[128];
+  alignas(16) float Tfin[128];
+  alignas(16) float bgs[256];
 };
 
 template <int NATOM>
@@ -101,6 +102,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     ctl.done_warps = 0; ctl.any_mma = 0;
     mbar_fence_init();
   }
+  if (tid < 256) ctl.bgs[tid] = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
   if (warp == 8) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
   tc_fence_before();
   __syncthreads();
@@ -136,31 +138,31 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float w[8];
+          // 8 independent alpha evaluations (no branches: keeps 8 dependency chains in flight)
+          float a[8];
+          int gi[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int g = c * 8 + k;
-            w[k] = 0.f;
-            if (g < nb) {
-              const int slot = (base + g) & (RING - 1);
-              const float4 r1 = rg1[slot];
-              if ((__float_as_uint(r1.w) >> pw) & 1u) {
-                const float4 r0 = rg0[slot];
-                if (!done) {
-                  const float a = eval_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, px, py);
-                  if (a > 0.f) {
-                    const float Tn = T * (1.f - a);
-                    if (Tn <= GAGS_T_STOP) {
-                      done = true;
-                    } else {
-                      w[k] = a * T;
-                      T = Tn;
-                      last = __float_as_int(r1.z);
-                    }
-                  }
-                }
-              }
-            }
+            const int slot = (base + g) & (RING - 1);
+            const float4 r0 = rg0[slot];
+            const float4 r1 = rg1[slot];
+            const float av = eval_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, px, py);
+            a[k] = (g < nb) ? av : 0.f;
+            gi[k] = __float_as_int(r1.z);
+          }
+          // sequential transmittance chain (selects only)
+          float w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float Tn = T * (1.f - a[k]);
+            const bool live = (a[k] > 0.f) && !done;
+            const bool stopnow = live && (Tn <= GAGS_T_STOP);
+            const bool take = live && !stopnow;
+            w[k] = take ? a[k] * T : 0.f;
+            T = take ? Tn : T;
+            last = take ? gi[k] : last;
+            done = done || stopnow;
           }
           uint4 h, l;
           split_pack2(w[0], w[1], h.x, l.x);
@@ -188,57 +190,74 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
   } else if (warp < 8) {
     // ======================= producer warps ========================================================
+    // Software pipeline per batch: (1) finish the pending scan round if the queue is short,
+    // (2) publish the batch list, (3) issue the feature-row loads, (4) issue the NEXT scan round's
+    // geometry loads, (5) split + store the feature rows, (6) signal the stage full.
     const int p = tid - 128, pw = warp - 4;
     const float hx0 = (float)x0 + 0.5f, hy0 = (float)y0 + 0.5f;
     int scan = s, qtail = 0, qhead = 0;
+    // pending scan round (loads in flight): candidate idx = pend_scan + p
+    bool pending = false;
+    int pend_idx = 0, pend_gid = 0;
+    float4 pa0 = make_float4(0.f, 0.f, 0.f, 0.f), pa1 = pa0;
+    int nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
+
+    auto issue_scan = [&]() {
+      pend_idx = scan + p;
+      pend_gid = nxt_gid;
+      if (pend_gid >= 0) {
+        pa0 = __ldg(geom + pend_gid * 2);
+        pa1 = __ldg(geom + pend_gid * 2 + 1);
+      }
+      scan += 128;
+      nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
+      pending = true;
+    };
+    auto finish_scan = [&]() {
+      bool keep = false;
+      unsigned mask = 0;
+      if (pend_gid >= 0) {
+        float hx, hy;
+        if (alpha_extent(pa0.z, pa0.w, pa1.x, pa1.y, hx, hy)) {
+          const float lx = pa0.x - hx, ux = pa0.x + hx, ly = pa0.y - hy, uy = pa0.y + hy;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
+            if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
+          }
+          keep = mask != 0u;
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) ctl.wcnt[pw] = __popc(bal);
+      named_bar_sync(1, 128);
+      int basec = qtail, total = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = ctl.wcnt[k];
+        if (k < pw) basec += c;
+        total += c;
+      }
+      if (keep) {
+        const int slot = (basec + __popc(bal & ((1u << lane) - 1u))) & (RING - 1);
+        rg0[slot] = pa0;
+        rg1[slot] = make_float4(pa1.x, pa1.y, __int_as_float(pend_idx), __uint_as_float(mask));
+        rgid[slot] = pend_gid;
+      }
+      qtail += total;
+      pending = false;
+      named_bar_sync(1, 128);
+    };
+
+    if (scan < e) issue_scan();
     for (int i = 0;; ++i) {
       const int st = i & 1;
-      const bool stop = *reinterpret_cast<volatile int *>(&ctl.done_warps) == 4;
-      // make the stop decision uniform over the 128 producer threads
-      if (lane == 0) ctl.wcnt[pw] = stop ? 1 : 0;
-      named_bar_sync(1, 128);
-      const bool stop_all = (ctl.wcnt[0] & ctl.wcnt[1] & ctl.wcnt[2] & ctl.wcnt[3]) != 0;
-      named_bar_sync(1, 128);
-      while (!stop_all && (qtail - qhead) < KB && scan < e) {
-        const int idx = scan + p;
-        bool keep = false;
-        unsigned mask = 0;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        int gid = 0;
-        if (idx < e) {
-          gid = ids[idx];
-          a0 = geom[gid * 2];
-          a1 = geom[gid * 2 + 1];
-          float hx, hy;
-          if (alpha_extent(a0.z, a0.w, a1.x, a1.y, hx, hy)) {
-            const float lx = a0.x - hx, ux = a0.x + hx, ly = a0.y - hy, uy = a0.y + hy;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
-              if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
-            }
-            keep = mask != 0u;
-          }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) ctl.wcnt[pw] = __popc(bal);
-        named_bar_sync(1, 128);
-        int basec = qtail, total = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = ctl.wcnt[k];
-          if (k < pw) basec += c;
-          total += c;
-        }
-        if (keep) {
-          const int slot = (basec + __popc(bal & ((1u << lane) - 1u))) & (RING - 1);
-          rg0[slot] = a0;
-          rg1[slot] = make_float4(a1.x, a1.y, __int_as_float(idx), __uint_as_float(mask));
-          rgid[slot] = gid;
-        }
-        qtail += total;
-        scan += 128;
-        named_bar_sync(1, 128);
+      // uniform stop decision: the pixel warps have all terminated
+      const int dw = *reinterpret_cast<volatile int *>(&ctl.done_warps);
+      const bool stop_all = named_bar_or(1, 128, dw == 4);
+      while (!stop_all && (qtail - qhead) < KB && (pending || scan < e)) {
+        if (!pending) issue_scan();
+        finish_scan();
       }
       const int nb = stop_all ? 0 : min(KB, qtail - qhead);
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
@@ -253,39 +272,36 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       unsigned char *blo = sB + (st * 2 + 1) * L::BPART;
       const int n0 = lane * 8;
       const int nbr = (nb + 15) & ~15;               // rows the MMAs will read
-      if (n0 < nch) {
-        const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
+      const bool chan_ok = n0 < nch;
+      const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
+      float4 v[8][2];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 v[4][2];
+      for (int j = 0; j < 8; ++j) {
+        const int kk = pw * 8 + j;
+        v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kk < nb && chan_ok) {
+          const int gid = rgid[(qhead + kk) & (RING - 1)];
+          const float4 *src = reinterpret_cast<const float4 *>(colors + (size_t)gid * D + ch0 + n0);
+          v[j][0] = __ldg(src);
+          v[j][1] = __ldg(src + 1);
+        }
+      }
+      // overlap the next scan round's geometry loads with the feature-row loads
+      if (!pending && (qtail - qhead - nb) < KB && scan < e) issue_scan();
+      if (chan_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kk = pw * 8 + half * 4 + j;
-            if (kk < nb) {
-              const int gid = rgid[(qhead + kk) & (RING - 1)];
-              const float4 *src =
-                  reinterpret_cast<const float4 *>(colors + (size_t)gid * D + ch0 + n0);
-              v[j][0] = __ldg(src);
-              v[j][1] = __ldg(src + 1);
-            } else {
-              v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kk = pw * 8 + half * 4 + j;
-            if (kk < nbr) {
-              uint4 h, l;
-              split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
-              split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
-              split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
-              split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
-              const uint32_t off =
-                  (uint32_t)(kk >> 3) * 1024u + sw128((uint32_t)(kk & 7) * 128u + (coff & 127u)) +
-                  (coff & ~127u);
-              *reinterpret_cast<uint4 *>(bhi + off) = h;
-              *reinterpret_cast<uint4 *>(blo + off) = l;
-            }
+        for (int j = 0; j < 8; ++j) {
+          const int kk = pw * 8 + j;
+          if (kk < nbr) {
+            uint4 h, l;
+            split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
+            split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
+            split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
+            split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
+            const uint32_t off = (uint32_t)(kk >> 3) * 1024u +
+                                 sw128((uint32_t)(kk & 7) * 128u + (coff & 127u)) + (coff & ~127u);
+            *reinterpret_cast<uint4 *>(bhi + off) = h;
+            *reinterpret_cast<uint4 *>(blo + off) = l;
           }
         }
       }
@@ -355,8 +371,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       for (int cc = 0; cc < 8; ++cc) {
         float4 v = make_float4(__uint_as_float(r[cc * 4]), __uint_as_float(r[cc * 4 + 1]),
                                __uint_as_float(r[cc * 4 + 2]), __uint_as_float(r[cc * 4 + 3]));
-        if (bg != nullptr && c0 + cc * 4 < nch) {
-          const float4 b = *reinterpret_cast<const float4 *>(bg + ch0 + c0 + cc * 4);
+        if (bg != nullptr) {
+          const float4 b = *reinterpret_cast<const float4 *>(&ctl.bgs[c0 + cc * 4]);
           v.x = fmaf(Tp, b.x, v.x); v.y = fmaf(Tp, b.y, v.y);
           v.z = fmaf(Tp, b.z, v.z); v.w = fmaf(Tp, b.w, v.w);
         }

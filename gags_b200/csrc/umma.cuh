@@ -109,3 +109,16 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t &hi, ui
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// named-barrier OR-reduction over `nthreads` threads (all of them must call it)
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
+      "setp.ne.u32 q, %3, 0;\n"
+      "bar.red.or.pred p, %1, %2, q;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}

@@ -186,8 +186,8 @@ def test_wide_blend_equals_channelwise_narrow():
         part, a2, _ = R._Blend.apply(st["means2d"], st["conics"], st["opac"],
                                      col[:, c0:c0 + 32].contiguous(), None, st["geom"],
                                      st["offsets"], st["flatten_ids"], W, H)
-        assert rel_err(wide[..., c0:c0 + 32], part) < 2e-6
-        assert torch.equal(a1, a2)
+        assert rel_err(wide[..., c0:c0 + 32], part) < 3e-5     # bf16 hi/lo split vs fp32 FMA
+        assert rel_err(a1, a2) < 1e-5
 
 
 @pytest.mark.parametrize("D", [3, 16, 32, 64, 128, 256, 512])
@@ -207,6 +207,34 @@ def test_feature_backward_matches_oracle(D):
                                st["offsets"], st["flatten_ids"], W, H)
     (out * v_out.cuda()).sum().backward()
     assert frac_bad(col_g.grad, cols.grad, RTOL) < 1e-4 and rel_err(col_g.grad, cols.grad) < 5e-3
+
+
+@pytest.mark.parametrize("D,n,opac_lo", [(48, 900, 0.05), (64, 900, 0.05), (128, 5000, 0.5),
+                                         (192, 900, 0.05), (256, 5000, 0.5), (512, 900, 0.05)])
+def test_tensor_core_feature_backward_matches_simt_and_oracle(D, n, opac_lo, blend_impl):
+    """tcgen05 feature backward vs the fp32 SIMT kernel and the fp64 oracle (autograd)."""
+    from gags_b200 import rasterization as R
+    W, H = 80, 56
+    sc = front_scene(n, W, H, D, seed=400 + D)
+    sc["opacities"] = sc["opacities"].clamp_min(opac_lo)
+    st = _stages(sc)
+    g = torch.Generator().manual_seed(2)
+    v_out = torch.randn(H, W, D, generator=g)
+    m2d, con, op, offs, ids = _blend_ref(st, None, None, W, H)
+    cols = sc["colors"].double().requires_grad_(True)
+    ref, _, _ = O.blend_fwd(m2d, con, cols, op, None, W, H, offs, ids)
+    (ref * v_out.double()).sum().backward()
+    grads = {}
+    for impl in (1, 2):
+        blend_impl(impl)
+        col_g = sc["colors"].cuda().requires_grad_(True)
+        out, _, _ = R._Blend.apply(st["means2d"], st["conics"], st["opac"], col_g, None, st["geom"],
+                                   st["offsets"], st["flatten_ids"], W, H)
+        (out * v_out.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        grads[impl] = col_g.grad
+    assert rel_err(grads[2], grads[1]) < 3e-5
+    assert frac_bad(grads[2], cols.grad, RTOL) < 1e-4 and rel_err(grads[2], cols.grad) < 5e-3
 
 
 @pytest.mark.parametrize("D", [3, 4, 16, 32, 64, 256])
