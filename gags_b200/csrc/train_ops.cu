@@ -47,14 +47,14 @@ l1_loss_kernel(const float4 *__restrict__ r, const float4 *__restrict__ t,
 __global__ void __launch_bounds__(256)
 adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
             float4 *__restrict__ v, long long n4, float step_size, float b1, float b2,
-            float inv_sqrt_bc2, float eps, int zero_grad) {
+            float omb1, float omb2, float inv_sqrt_bc2, float eps, int zero_grad) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 gi = g[i];
     float4 mi = m[i], vi = v[i], pi = p[i];
 #define GAGS_ADAM1(c)                                             \
-    mi.c = b1 * mi.c + (1.f - b1) * gi.c;                         \
-    vi.c = b2 * vi.c + (1.f - b2) * gi.c * gi.c;                  \
+    mi.c = b1 * mi.c + omb1 * gi.c;                               \
+    vi.c = b2 * vi.c + omb2 * (gi.c * gi.c);                      \
     pi.c -= step_size * (mi.c / (sqrtf(vi.c) * inv_sqrt_bc2 + eps));
     GAGS_ADAM1(x) GAGS_ADAM1(y) GAGS_ADAM1(z) GAGS_ADAM1(w)
 #undef GAGS_ADAM1
@@ -64,19 +64,46 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
 }
 
 __global__ void adam_tail_kernel(float *p, float *g, float *m, float *v, long long start,
-                                 long long n, float step_size, float b1, float b2,
-                                 float inv_sqrt_bc2, float eps, int zero_grad) {
+                                 long long n, float step_size, float b1, float b2, float omb1,
+                                 float omb2, float inv_sqrt_bc2, float eps, int zero_grad) {
   const long long i = start + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i];
-  const float mi = b1 * m[i] + (1.f - b1) * gi;
-  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  const float mi = b1 * m[i] + omb1 * gi;
+  const float vi = b2 * v[i] + omb2 * (gi * gi);
   p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
   m[i] = mi; v[i] = vi;
   if (zero_grad) g[i] = 0.f;
 }
 
+// v *= *scale, skipped entirely (one 4-byte read per thread block) when *scale == 1: the usual
+// loss.backward() seeds the graph with ones, so the fused loss's gradient is already final.
+__global__ void __launch_bounds__(256)
+scale_dev_kernel(float4 *__restrict__ v, const float *__restrict__ scale, long long n4) {
+  const float s = __ldg(scale);
+  if (s == 1.f) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 x = v[i];
+    x.x *= s; x.y *= s; x.z *= s; x.w *= s;
+    v[i] = x;
+  }
+}
+
 }  // namespace
+
+extern "C" int gags_scale_inplace(float *v, const float *scale_dev, int64_t numel, void *stream) {
+  if (!v || !scale_dev || numel < 0 || (numel & 3)) return GAGS_EINVAL;
+  if (!gags_aligned16(v)) return GAGS_EALIGN;
+  if (numel == 0) return 0;
+  const long long n4 = numel / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  scale_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4 *>(v), scale_dev, n4);
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int gags_l1_loss_fused(const float *render, const float *target, const float *mask,
                                   int64_t HW, int32_t D, float grad_scale, float *loss_out,
@@ -96,17 +123,19 @@ extern "C" int gags_l1_loss_fused(const float *render, const float *target, cons
 }
 
 extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
-                              int64_t numel, float lr, float beta1, float beta2, float eps,
+                              int64_t numel, double lr, double beta1, double beta2, double eps,
                               int32_t step, int32_t zero_grad, void *stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || numel < 0 || step < 1) return GAGS_EINVAL;
   if (!gags_aligned16(param) || !gags_aligned16(grad) || !gags_aligned16(exp_avg) ||
       !gags_aligned16(exp_avg_sq))
     return GAGS_EALIGN;
   if (numel == 0) return 0;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  // 1 - beta in double, as torch does (1.f - 0.999f is off by 5e-5 relative)
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long n4 = numel / 4;
   cudaStream_t st = (cudaStream_t)stream;
   if (n4 > 0) {
@@ -115,12 +144,13 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
     adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),
         reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), n4, step_size,
-        beta1, beta2, inv_sqrt_bc2, eps, zero_grad);
+        (float)beta1, (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps, zero_grad);
     GAGS_CHECK_LAUNCH();
   }
   if (n4 * 4 < numel) {
     adam_tail_kernel<<<1, 32, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4 * 4, numel, step_size,
-                                       beta1, beta2, inv_sqrt_bc2, eps, zero_grad);
+                                       (float)beta1, (float)beta2, omb1, omb2, inv_sqrt_bc2,
+                                       (float)eps, zero_grad);
     GAGS_CHECK_LAUNCH();
   }
   return 0;

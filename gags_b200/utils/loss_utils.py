@@ -46,8 +46,15 @@ class _L1Fused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        # chain with the incoming grad_output on the device; when it is the usual 1.0 the stored
+        # gradient is returned untouched (no 2 GB multiply pass).  The buffer is scaled in place,
+        # so this node supports a single backward (no retain_graph re-entry).
         (v,) = ctx.saved_tensors
-        return v * g, None, None
+        gs = g.detach().reshape(1).to(torch.float32).contiguous()
+        _C.check(_C.lib.gags_scale_inplace(_C.ptr(v), _C.ptr(gs), v.numel(), _C.stream_ptr()),
+                 "gags_scale_inplace")
+        _C.count_launch()
+        return v, None, None
 
 
 def l1_loss_fused(render_dhw, gt_hwd, mask_hw=None):

@@ -173,12 +173,17 @@ int gags_l1_loss_fused(const float *render, const float *target, const float *ma
                        int32_t D, float grad_scale, float *loss_out, float *v_render,
                        void *stream);
 
+/* v[0..numel) *= *scale_dev (a DEVICE scalar), a no-op pass when the scalar is exactly 1: chains the
+ * fused loss's stored gradient with autograd's incoming grad_output without a host sync and, in the
+ * usual loss.backward() case, without touching the 2 GB buffer.  numel % 4 == 0.                */
+int gags_scale_inplace(float *v, const float *scale_dev, int64_t numel, void *stream);
+
 /* §8f-2  fused Adam on the per-Gaussian feature table (replaces torch.optim.Adam(lr, eps=1e-15)
  * on _semantic_feature, /root/reference/scene/gaussian_model.py:199,208; train.py:222-223).
  * Updates param/m/v in place; if zero_grad != 0 the gradient is zeroed in the same pass.       */
 int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t numel,
-                   float lr, float beta1, float beta2, float eps, int32_t step, int32_t zero_grad,
-                   void *stream);
+                   double lr, double beta1, double beta2, double eps, int32_t step,
+                   int32_t zero_grad, void *stream);
 
 #ifdef __cplusplus
 }

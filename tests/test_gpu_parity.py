@@ -443,6 +443,20 @@ def test_geometry_gradients_end_to_end_rgb():
     assert pkg["viewspace_points"].grad is not None
 
 
+def test_fused_l1_chains_grad_output():
+    """the fused L1's stored gradient is scaled on the device by whatever autograd sends in."""
+    from gags_b200.utils.loss_utils import l1_loss, l1_loss_fused
+    g = torch.Generator().manual_seed(3)
+    r = torch.randn(20, 24, 16, generator=g).cuda()
+    t = torch.randn(20, 24, 16, generator=g).cuda()
+    for scale in (1.0, 2.5):
+        a = r.clone().requires_grad_(True)
+        b = r.clone().requires_grad_(True)
+        (scale * l1_loss_fused(a.permute(2, 0, 1), t)).backward()
+        (scale * l1_loss(b.permute(2, 0, 1), t.permute(2, 0, 1))).backward()
+        assert rel_err(a.grad, b.grad) < 1e-6
+
+
 def test_fused_adam_matches_torch_adam():
     from gags_b200.optim import FusedAdam
     g = torch.Generator().manual_seed(8)
