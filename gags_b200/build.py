@@ -29,16 +29,20 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
+def build(force: bool = False, verbose: bool = False, timing: bool = False) -> str:
+    """timing=True builds csrc/libgags_b200_dbg.so with -DGAGS_TC_TIMING (tools/tc_timeline.py)."""
+    lib = LIB.replace(".so", "_dbg.so") if timing else LIB
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _deps_mtime():
+        return lib
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build_dbg" if timing else "build")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if timing:
+            cmd.insert(1, "-DGAGS_TC_TIMING")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,12 +54,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-gencode",
+    r = subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-gencode",
                         "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                timing="--timing" in sys.argv))

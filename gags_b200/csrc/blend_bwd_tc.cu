@@ -22,12 +22,12 @@
 //
 // Roofline: HBM — H*W*4D (v_render, once) + N_contrib*4D*2 (reduction target; the reductions resolve
 // in L2) + 12 B per list entry scanned.
-#include "umma.cuh"
+#include "blend_tc_common.cuh"
 
 namespace {
 
-constexpr int KB = 32;
-constexpr int RING = 256;
+constexpr int KB = TC_KB;
+constexpr int RING = TC_RING;
 constexpr int BW_THREADS = 416;
 
 struct BwCtl {
@@ -38,6 +38,8 @@ struct BwCtl {
   int wcnt[4];
   int bcnt[4], bskip[4];
   int bgid[4][KB];
+  alignas(16) float4 rec0[2][KB];     // per-stage batch records read by the pixel threads
+  alignas(16) float4 rec1[2][KB];
 };
 
 template <int MB>
@@ -51,22 +53,6 @@ struct BwLayout {
   static constexpr int BYTES = CTL_OFF + (int)sizeof(BwCtl) + 1024;
   static constexpr int TCOLS = MB == 1 ? 128 : 256;    // 2 buffers x MB x 64 columns
 };
-
-__device__ __forceinline__ bool alpha_extent_b(float a, float b, float c, float op, float &hx,
-                                               float &hy) {
-  const float L = __logf(255.f * op);
-  if (!(L > -1e-3f)) return false;
-  const float Lm = fmaxf(L, 0.f) + 2e-3f;
-  const float det = a * c - b * b;
-  if (det > 0.f) {
-    const float inv = 2.f * Lm / det;
-    hx = sqrtf(inv * c) * 1.0005f + 0.02f;
-    hy = sqrtf(inv * a) * 1.0005f + 0.02f;
-  } else {
-    hx = hy = 1e9f;
-  }
-  return true;
-}
 
 template <int MB>
 __global__ void __launch_bounds__(BW_THREADS, 1)
@@ -117,59 +103,35 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
     const int pxi = x0 + dx, pyi = y0 + dy;
     const bool inside = (pxi < W) && (pyi < H);
     const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
-    float T = 1.f;
-    bool done = !inside, counted = false;
+    TcPixel ps;
+    ps.px = px; ps.py = py; ps.T = 1.f; ps.last = 0; ps.done = !inside;
+    bool counted = false;
     const uint32_t rowoff = (uint32_t)tid * 128u;
     for (int i = 0;; ++i) {
       const int st = i & 1;
       mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
       const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
       if (nb == 0) break;
-      const int base = *reinterpret_cast<volatile int *>(&ctl.gbase[st]);
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
       unsigned char *wrow = sW + st * 16384;
-      const bool wdone = __all_sync(0xffffffffu, done);
+      const bool wdone = __all_sync(0xffffffffu, ps.done);
       if (wdone) {
         if (lane == 0) atomicAdd(&ctl.skip[st], 1);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(wrow + sw128(rowoff + c * 16)) = z;
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          float a[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int g = c * 8 + k;
-            const int slot = (base + g) & (RING - 1);
-            const float4 r0 = rg0[slot];
-            const float4 r1 = rg1[slot];
-            const float av = eval_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, px, py);
-            a[k] = (g < nb) ? av : 0.f;
-          }
-          float w[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float Tn = T * (1.f - a[k]);
-            const bool live = (a[k] > 0.f) && !done;
-            const bool stopnow = live && (Tn <= GAGS_T_STOP);
-            const bool take = live && !stopnow;
-            w[k] = take ? a[k] * T : 0.f;
-            T = take ? Tn : T;
-            done = done || stopnow;
-          }
           uint4 h, l;
-          split_pack2(w[0], w[1], h.x, l.x);
-          split_pack2(w[2], w[3], h.y, l.y);
-          split_pack2(w[4], w[5], h.z, l.z);
-          split_pack2(w[6], w[7], h.w, l.w);
+          tc_weights8(&ctl.rec0[st][c * 8], &ctl.rec1[st][c * 8], ps, h, l);
           *reinterpret_cast<uint4 *>(wrow + sw128(rowoff + c * 16)) = h;
           *reinterpret_cast<uint4 *>(wrow + sw128(rowoff + (c + 4) * 16)) = l;
         }
       }
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
-      if (!counted && __all_sync(0xffffffffu, done)) {
+      if (!counted && __all_sync(0xffffffffu, ps.done)) {
         counted = true;
         if (lane == 0) atomicAdd(&ctl.done_warps, 1);
       }
@@ -196,20 +158,8 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
       pending = true;
     };
     auto finish_scan = [&]() {
-      bool keep = false;
-      unsigned mask = 0;
-      if (pend_gid >= 0) {
-        float hx, hy;
-        if (alpha_extent_b(pa0.z, pa0.w, pa1.x, pa1.y, hx, hy)) {
-          const float lx = pa0.x - hx, ux = pa0.x + hx, ly = pa0.y - hy, uy = pa0.y + hy;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
-            if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
-          }
-          keep = mask != 0u;
-        }
-      }
+      const unsigned mask = (pend_gid >= 0) ? tc_block_mask(pa0, pa1, hx0, hy0) : 0u;
+      const bool keep = mask != 0u;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (lane == 0) ctl.wcnt[pw] = __popc(bal);
       named_bar_sync(1, 128);
@@ -249,7 +199,16 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
         ctl.gbase[st] = qhead & (RING - 1);
         ctl.bcnt[i & 3] = nb;
       }
-      if (p < nb) ctl.bgid[i & 3][p] = rgid[(qhead + p) & (RING - 1)];
+      if (p < KB) {
+        TcRec r = tc_null_rec();
+        if (p < nb) {
+          const int slot = (qhead + p) & (RING - 1);
+          r = tc_make_rec(rg0[slot], rg1[slot]);
+          ctl.bgid[i & 3][p] = rgid[slot];
+        }
+        ctl.rec0[st][p] = r.q0;
+        ctl.rec1[st][p] = r.q1;
+      }
       mbar_arrive(&ctl.list[st]);
       if (nb == 0) break;
       qhead += nb;
@@ -347,7 +306,8 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
     if (lane == 0) {
       const uint32_t idesc64 = umma_idesc_bf16(64, true, true);
       const uint32_t idesc32 = umma_idesc_bf16(32, true, true);
-      const uint32_t v_addr = smem_u32(sV), w_addr = smem_u32(sW);
+      const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 16384, 1024);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW), 16, 1024);
       int seen[2] = {0, 0};
       bool vready = false;
       for (int i = 0;; ++i) {
@@ -375,10 +335,9 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
           for (int mb = 0; mb < MB; ++mb) {
             const uint32_t d = tb + (uint32_t)(buf * (MB * 64) + mb * 64);
             for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ahi = umma_desc_sw128(v_addr + mb * 32768 + ks * 2048, 16384, 1024);
-              const uint64_t alo =
-                  umma_desc_sw128(v_addr + L::VPART + mb * 32768 + ks * 2048, 16384, 1024);
-              const uint64_t bw = umma_desc_sw128(w_addr + st * 16384 + ks * 2048, 16, 1024);
+              const uint64_t ahi = v_desc0 + (uint64_t)((mb * 32768 + ks * 2048) >> 4);
+              const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
+              const uint64_t bw = w_desc0 + (uint64_t)((st * 16384 + ks * 2048) >> 4);
               umma_bf16_ss(d, ahi, bw, idesc64, ks > 0 ? 1u : 0u);
               umma_bf16_ss(d, alo, bw, idesc32, 1u);
             }

@@ -24,12 +24,28 @@
 //
 // Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
 // hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
-#include "umma.cuh"
+#include "blend_tc_common.cuh"
+
+// Optional timeline instrumentation (tools/tc_timeline.py builds a second library with
+// -DGAGS_TC_TIMING): selected CTAs stamp clock64() at role milestones into a global buffer.
+#ifdef GAGS_TC_TIMING
+__device__ long long g_tc_dbg[8 * 4 * 64 * 8];     // [cta slot][role][batch][event]
+extern "C" int gags_debug_timeline(long long *host_dst, int n) {
+  return (int)cudaMemcpyFromSymbol(host_dst, g_tc_dbg, sizeof(long long) * (size_t)n);
+}
+#define TC_STAMP(role, batch, ev)                                                              \
+  do {                                                                                         \
+    if (dbg_slot >= 0 && lane == 0 && (batch) < 64)                                            \
+      g_tc_dbg[((dbg_slot * 4 + (role)) * 64 + (batch)) * 8 + (ev)] = clock64();              \
+  } while (0)
+#else
+#define TC_STAMP(role, batch, ev) do { } while (0)
+#endif
 
 namespace {
 
-constexpr int KB = 32;        // Gaussians per batch (= one 128-B row of [hi|lo] bf16 weights)
-constexpr int RING = 256;     // survivor ring capacity (power of two)
+constexpr int KB = TC_KB;
+constexpr int RING = TC_RING;
 constexpr int TC_THREADS = 288;
 
 struct TcCtl {
@@ -41,6 +57,8 @@ struct TcCtl {
   int wcnt[4];
   alignas(16) float Tfin[128];
   alignas(16) float bgs[256];
+  alignas(16) float4 rec0[2][KB];     // per-stage batch records read by the pixel threads
+  alignas(16) float4 rec1[2][KB];
 };
 
 template <int NATOM>
@@ -53,23 +71,6 @@ struct TcLayout {
   static constexpr int BYTES = CTL_OFF + (int)sizeof(TcCtl) + 1024;   // + alignment slack
   static constexpr int TCOLS = NATOM == 1 ? 64 : (NATOM == 2 ? 128 : 256);
 };
-
-// conservative reach of the alpha >= 1/255 ellipse; returns false when the Gaussian can never pass
-__device__ __forceinline__ bool alpha_extent(float a, float b, float c, float op, float &hx,
-                                             float &hy) {
-  const float L = __logf(255.f * op);
-  if (!(L > -1e-3f)) return false;
-  const float Lm = fmaxf(L, 0.f) + 2e-3f;
-  const float det = a * c - b * b;
-  if (det > 0.f) {
-    const float inv = 2.f * Lm / det;
-    hx = sqrtf(inv * c) * 1.0005f + 0.02f;
-    hy = sqrtf(inv * a) * 1.0005f + 0.02f;
-  } else {
-    hx = hy = 1e9f;
-  }
-  return true;
-}
 
 template <int NATOM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -91,6 +92,15 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   const int tile = (blockIdx.y >> 1) * tile_w + blockIdx.x;
   const int x0 = blockIdx.x * GAGS_TILE, y0 = blockIdx.y * 8;
   const int s = offsets[tile], e = offsets[tile + 1];
+#ifdef GAGS_TC_TIMING
+  // 8 sampled CTAs spread over the grid
+  int dbg_slot = -1;
+  {
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x, tot = gridDim.x * gridDim.y;
+    for (int k = 0; k < 8; ++k) if (lin == (tot / 9) * (k + 1)) dbg_slot = k;
+  }
+  TC_STAMP(3, 0, 0);
+#endif
 
   if (tid == 0) {
     for (int k = 0; k < 2; ++k) {
@@ -116,70 +126,46 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     const int pxi = x0 + dx, pyi = y0 + dy;
     const bool inside = (pxi < W) && (pyi < H);
     const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
-    float T = 1.f;
-    int last = 0;
-    bool done = !inside, counted = false;
+    TcPixel ps;
+    ps.px = px; ps.py = py; ps.T = 1.f; ps.last = 0; ps.done = !inside;
+    bool counted = false;
     const uint32_t rowoff = (uint32_t)tid * 128u;
     int i = 0;
     for (;; ++i) {
       const int st = i & 1;
+      if (warp == 0) TC_STAMP(0, i, 0);
       mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
+      if (warp == 0) TC_STAMP(0, i, 1);
       const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
       if (nb == 0) break;
-      const int base = *reinterpret_cast<volatile int *>(&ctl.gbase[st]);
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+      if (warp == 0) TC_STAMP(0, i, 2);
       unsigned char *arow = sA + st * 16384;
-      const bool wdone = __all_sync(0xffffffffu, done);
+      const bool wdone = __all_sync(0xffffffffu, ps.done);
       if (wdone) {
         if (lane == 0) atomicAdd(&ctl.skip[st], 1);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = z;
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          // 8 independent alpha evaluations (no branches: keeps 8 dependency chains in flight)
-          float a[8];
-          int gi[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int g = c * 8 + k;
-            const int slot = (base + g) & (RING - 1);
-            const float4 r0 = rg0[slot];
-            const float4 r1 = rg1[slot];
-            const float av = eval_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, px, py);
-            a[k] = (g < nb) ? av : 0.f;
-            gi[k] = __float_as_int(r1.z);
-          }
-          // sequential transmittance chain (selects only)
-          float w[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float Tn = T * (1.f - a[k]);
-            const bool live = (a[k] > 0.f) && !done;
-            const bool stopnow = live && (Tn <= GAGS_T_STOP);
-            const bool take = live && !stopnow;
-            w[k] = take ? a[k] * T : 0.f;
-            T = take ? Tn : T;
-            last = take ? gi[k] : last;
-            done = done || stopnow;
-          }
           uint4 h, l;
-          split_pack2(w[0], w[1], h.x, l.x);
-          split_pack2(w[2], w[3], h.y, l.y);
-          split_pack2(w[4], w[5], h.z, l.z);
-          split_pack2(w[6], w[7], h.w, l.w);
+          tc_weights8(&ctl.rec0[st][c * 8], &ctl.rec1[st][c * 8], ps, h, l);
           *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = h;
           *reinterpret_cast<uint4 *>(arow + sw128(rowoff + (c + 4) * 16)) = l;
         }
       }
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
-      if (!counted && __all_sync(0xffffffffu, done)) {
+      if (warp == 0) TC_STAMP(0, i, 3);
+      if (!counted && __all_sync(0xffffffffu, ps.done)) {
         counted = true;
         if (lane == 0) atomicAdd(&ctl.done_warps, 1);
       }
     }
+    const float T = ps.T;
+    const int last = ps.last;
     ctl.Tfin[tid] = T;
     if (inside && ch0 == 0) {
       const size_t pix = (size_t)pyi * W + pxi;
@@ -214,20 +200,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       pending = true;
     };
     auto finish_scan = [&]() {
-      bool keep = false;
-      unsigned mask = 0;
-      if (pend_gid >= 0) {
-        float hx, hy;
-        if (alpha_extent(pa0.z, pa0.w, pa1.x, pa1.y, hx, hy)) {
-          const float lx = pa0.x - hx, ux = pa0.x + hx, ly = pa0.y - hy, uy = pa0.y + hy;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
-            if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
-          }
-          keep = mask != 0u;
-        }
-      }
+      const unsigned mask = (pend_gid >= 0) ? tc_block_mask(pa0, pa1, hx0, hy0) : 0u;
+      const bool keep = mask != 0u;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (lane == 0) ctl.wcnt[pw] = __popc(bal);
       named_bar_sync(1, 128);
@@ -253,17 +227,29 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     for (int i = 0;; ++i) {
       const int st = i & 1;
       // uniform stop decision: the pixel warps have all terminated
+      if (warp == 4) TC_STAMP(1, i, 0);
       const int dw = *reinterpret_cast<volatile int *>(&ctl.done_warps);
       const bool stop_all = named_bar_or(1, 128, dw == 4);
       while (!stop_all && (qtail - qhead) < KB && (pending || scan < e)) {
         if (!pending) issue_scan();
         finish_scan();
       }
+      if (warp == 4) TC_STAMP(1, i, 1);
       const int nb = stop_all ? 0 : min(KB, qtail - qhead);
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+      if (warp == 4) TC_STAMP(1, i, 2);
       if (p == 0) {
         ctl.gcount[st] = nb;
         ctl.gbase[st] = qhead & (RING - 1);
+      }
+      if (p < KB) {
+        TcRec r = tc_null_rec();
+        if (p < nb) {
+          const int slot = (qhead + p) & (RING - 1);
+          r = tc_make_rec(rg0[slot], rg1[slot]);
+        }
+        ctl.rec0[st][p] = r.q0;
+        ctl.rec1[st][p] = r.q1;
       }
       mbar_arrive(&ctl.list[st]);
       if (nb == 0) break;
@@ -286,6 +272,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           v[j][1] = __ldg(src + 1);
         }
       }
+      if (warp == 4) TC_STAMP(1, i, 3);
       // overlap the next scan round's geometry loads with the feature-row loads
       if (!pending && (qtail - qhead - nb) < KB && scan < e) issue_scan();
       if (chan_ok) {
@@ -307,13 +294,15 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       }
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
+      if (warp == 4) TC_STAMP(1, i, 4);
       qhead += nb;
     }
   } else {
     // ======================= MMA issuer ============================================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(nch, false, true);
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB), 4096, 1024);
       uint32_t acc = 0;
       int seen[2] = {0, 0};
       for (int i = 0;; ++i) {
@@ -321,7 +310,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
         const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
         if (nb == 0) break;
+        TC_STAMP(2, i, 0);
         mbar_wait_bounded(&ctl.full[st], (i >> 1) & 1);
+        TC_STAMP(2, i, 1);
         tc_fence_after();
         const int votes_now = *reinterpret_cast<volatile int *>(&ctl.skip[st]);
         const int votes = votes_now - seen[st];
@@ -329,12 +320,11 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         if (votes < 4) {
           const int nk = (nb + 15) >> 4;
           for (int ks = 0; ks < nk; ++ks) {
-            const uint64_t ahi = umma_desc_sw128(a_addr + st * 16384 + ks * 32, 16, 1024);
-            const uint64_t alo = umma_desc_sw128(a_addr + st * 16384 + 64 + ks * 32, 16, 1024);
-            const uint64_t bhi =
-                umma_desc_sw128(b_addr + (st * 2 + 0) * L::BPART + ks * 2048, 4096, 1024);
-            const uint64_t blo =
-                umma_desc_sw128(b_addr + (st * 2 + 1) * L::BPART + ks * 2048, 4096, 1024);
+            // only the 14-bit start-address field (16-B units) changes between descriptors
+            const uint64_t ahi = a_desc0 + (uint64_t)((st * 16384 + ks * 32) >> 4);
+            const uint64_t alo = ahi + (uint64_t)(64 >> 4);
+            const uint64_t bhi = b_desc0 + (uint64_t)(((st * 2) * L::BPART + ks * 2048) >> 4);
+            const uint64_t blo = bhi + (uint64_t)(L::BPART >> 4);
             umma_bf16_ss(tb, ahi, bhi, idesc, acc);
             acc = 1;
             umma_bf16_ss(tb, ahi, blo, idesc, 1);
@@ -342,6 +332,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           }
         }
         umma_commit(&ctl.free_[st]);
+        TC_STAMP(2, i, 2);
       }
       ctl.any_mma = (int)acc;
     }
@@ -349,9 +340,11 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   }
 
   // ========================= epilogue: TMEM -> registers -> smem transpose -> HBM ==================
+  if (warp == 0) TC_STAMP(3, 0, 1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp == 0) TC_STAMP(3, 0, 2);
   if (warp < 8) {
     const bool any = ctl.any_mma != 0;
     const int q = warp & 3, half = warp >> 2;
@@ -391,6 +384,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       __syncwarp();
     }
   }
+  if (warp == 0) TC_STAMP(3, 0, 3);
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<L::TCOLS>(tb);

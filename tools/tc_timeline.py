@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Per-role cycle timeline of a few CTAs of blend_fwd_tc on the config-3 scene (debug library built
+with `python -m gags_b200.build --timing`).  Run on the GPU box."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["GAGS_B200_LIB"] = os.path.join(ROOT, "gags_b200", "csrc", "libgags_b200_dbg.so")
+import torch
+from gags_b200 import _C
+from gags_b200.gaussian_renderer import render
+from gags_b200.scene import GaussianModel
+from gags_b200.synthetic import config_scene
+
+dev = torch.device("cuda:0")
+scene = config_scene(3)
+pc = GaussianModel(3, device=dev)
+pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity, scene.features_dc,
+                       scene.features_rest, scene.semantic_feature)
+cam = scene.cameras[0].to(dev)
+bg = torch.zeros(3, device=dev)
+with torch.no_grad():
+    for _ in range(3):
+        render(cam, pc, None, bg)
+torch.cuda.synchronize()
+n = 8 * 4 * 64 * 8
+buf = (ctypes.c_longlong * n)()
+_C.lib.gags_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+rc = _C.lib.gags_debug_timeline(buf, n)
+assert rc == 0, rc
+t = torch.tensor(list(buf), dtype=torch.int64).reshape(8, 4, 64, 8)
+names = {0: ["top", "list_ok", "free_ok", "stored"], 1: ["top", "scanned", "free_ok", "loads_issued", "stored"],
+         2: ["wait_full", "full_ok", "committed"]}
+for slot in range(8):
+    t0 = int(t[slot, 3, 0, 0])
+    if t0 == 0:
+        continue
+    print(f"=== CTA slot {slot}: epilogue-sync at +{int(t[slot,3,0,1])-t0}, after-sync +{int(t[slot,3,0,2])-t0}, end +{int(t[slot,3,0,3])-t0}")
+    for b in range(64):
+        if t[slot, 0, b, 0] == 0 and t[slot, 1, b, 0] == 0:
+            break
+        line = f" b{b:2d} "
+        for role, tag in ((1, "prod"), (0, "pix"), (2, "mma")):
+            vals = [int(x) - t0 if x else -1 for x in t[slot, role, b, :len(names[role])]]
+            line += f"| {tag} " + " ".join(f"{v:6d}" for v in vals) + " "
+        print(line)
