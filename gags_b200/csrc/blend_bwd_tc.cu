@@ -104,7 +104,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
     const bool inside = (pxi < W) && (pyi < H);
     const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
     TcPixel ps;
-    ps.px = px; ps.py = py; ps.T = 1.f; ps.last = 0; ps.done = !inside;
+    tc_pixel_init(ps, px, py, inside);
     bool counted = false;
     const uint32_t rowoff = (uint32_t)tid * 128u;
     for (int i = 0;; ++i) {
@@ -114,7 +114,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
       if (nb == 0) break;
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
       unsigned char *wrow = sW + st * 16384;
-      const bool wdone = __all_sync(0xffffffffu, ps.done);
+      const bool wdone = __all_sync(0xffffffffu, tc_pixel_done(ps));
       if (wdone) {
         if (lane == 0) atomicAdd(&ctl.skip[st], 1);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -131,7 +131,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
       }
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
-      if (!counted && __all_sync(0xffffffffu, ps.done)) {
+      if (!counted && __all_sync(0xffffffffu, tc_pixel_done(ps))) {
         counted = true;
         if (lane == 0) atomicAdd(&ctl.done_warps, 1);
       }

@@ -9,18 +9,20 @@
 // products hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (measured 4e-6 relative,
 // tools/umma_probe.cu).
 //
-// One CTA = one half tile, 9 warps, warp-specialised, two smem stages of 32 Gaussians:
-//   warps 4-7  producers: scan the tile list 128 entries at a time, cull every Gaussian whose
-//              alpha >= 1/255 ellipse misses the half tile (exact: such a Gaussian contributes to no
-//              pixel), append survivors (+ a 4-bit mask of the 8x4 pixel blocks it can touch) to a
-//              ring; per batch gather the survivors' feature rows with coalesced 32-B loads, split
-//              them to bf16 hi/lo in registers and store them in the MN-major SWIZZLE_128B layout.
-//   warps 0-3  one thread per pixel: evaluate alpha, run the transmittance chain, write the
-//              weight row [hi(32) | lo(32)] (128 B, K-major SWIZZLE_128B).
-//   warp 8     one thread issues tcgen05.mma (M=128, N=D, K=16) x 3 products x 2 k-steps per batch;
-//              tcgen05.commit frees the stage.
-// Epilogue: tcgen05.ld -> + T*background -> per-warp transpose in smem -> 128-B coalesced
-// streaming stores of the channel-last raster.
+// One CTA = one half tile, 13 warps, warp-specialised, two smem stages of 32 Gaussians:
+//   warps 4-7   scanner: walks the tile list 128 entries at a time, culls every Gaussian whose
+//               alpha >= 1/255 ellipse misses the half tile (exact), keeps the survivors in a ring
+//               and publishes one batch (32 blend records + Gaussian ids) per stage.
+//   warps 8-11  converters: gather the batch's feature rows with coalesced 32-B loads, four rows
+//               in flight per thread in a rolling register ring that runs across batch boundaries
+//               (the next batch's rows are already loading while this one is split), split them to
+//               bf16 hi/lo in registers and store them in the MN-major SWIZZLE_128B layout.
+//   warps 0-3   one thread per pixel: evaluate alpha, transmittance product, write the weight row
+//               [hi(32) | lo(32)] (128 B, K-major SWIZZLE_128B).
+//   warp 12     one thread issues tcgen05.mma (M=128, N=D, K=16) x 3 products x 2 k-steps per batch;
+//               tcgen05.commit frees the stage.
+// Epilogue (warps 0-11): tcgen05.ld -> + T*background -> per-warp transpose in smem -> 128-B
+// coalesced streaming stores of the channel-last raster.
 //
 // Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
 // hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
@@ -46,15 +48,16 @@ namespace {
 
 constexpr int KB = TC_KB;
 constexpr int RING = TC_RING;
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;
 
 struct TcCtl {
   uint64_t list[2], full[2], free_[2];
   uint32_t tmem_base;
-  int gcount[2], gbase[2];
+  int gcount[2];
   int skip[2];
-  int done_warps, any_mma;
+  int done_warps, skip_from, any_mma;
   int wcnt[4];
+  int gid[2][KB];
   alignas(16) float Tfin[128];
   alignas(16) float bgs[256];
   alignas(16) float4 rec0[2][KB];     // per-stage batch records read by the pixel threads
@@ -67,10 +70,13 @@ struct TcLayout {
   static constexpr int A_OFF = 0;                      // 2 stages x 16 KB
   static constexpr int B_OFF = 32768;                  // [stage][part][BPART]
   static constexpr int RING_OFF = B_OFF + 4 * BPART;
-  static constexpr int CTL_OFF = RING_OFF + RING * 36;
+  static constexpr int STG_END = 12 * 4096;            // epilogue staging: 12 warps x 4 KB from 0
+  static constexpr int CTL_OFF = (RING_OFF + RING * 36) > STG_END ? (RING_OFF + RING * 36) : STG_END;
   static constexpr int BYTES = CTL_OFF + (int)sizeof(TcCtl) + 1024;   // + alignment slack
   static constexpr int TCOLS = NATOM == 1 ? 64 : (NATOM == 2 ? 128 : 256);
 };
+// two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
+static_assert(TcLayout<4>::BYTES <= (233472 / 2 - 1024), "forward TC kernel must fit twice per SM");
 
 template <int NATOM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -107,13 +113,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       mbar_init(&ctl.list[k], 128);
       mbar_init(&ctl.full[k], 256);
       mbar_init(&ctl.free_[k], 1);
-      ctl.gcount[k] = 0; ctl.gbase[k] = 0; ctl.skip[k] = 0;
+      ctl.gcount[k] = 0; ctl.skip[k] = 0;
     }
-    ctl.done_warps = 0; ctl.any_mma = 0;
+    ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0;
     mbar_fence_init();
   }
   if (tid < 256) ctl.bgs[tid] = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
-  if (warp == 8) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  if (warp == 12) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,9 +131,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
     const int pxi = x0 + dx, pyi = y0 + dy;
     const bool inside = (pxi < W) && (pyi < H);
-    const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
     TcPixel ps;
-    ps.px = px; ps.py = py; ps.T = 1.f; ps.last = 0; ps.done = !inside;
+    tc_pixel_init(ps, (float)pxi + 0.5f, (float)pyi + 0.5f, inside);
     bool counted = false;
     const uint32_t rowoff = (uint32_t)tid * 128u;
     int i = 0;
@@ -138,10 +143,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (warp == 0) TC_STAMP(0, i, 1);
       const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
       if (nb == 0) break;
-      if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
-      if (warp == 0) TC_STAMP(0, i, 2);
       unsigned char *arow = sA + st * 16384;
-      const bool wdone = __all_sync(0xffffffffu, ps.done);
+      const bool wdone = __all_sync(0xffffffffu, tc_pixel_done(ps));
       if (wdone) {
         if (lane == 0) atomicAdd(&ctl.skip[st], 1);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -159,143 +162,140 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
       if (warp == 0) TC_STAMP(0, i, 3);
-      if (!counted && __all_sync(0xffffffffu, ps.done)) {
+      if (!counted && __all_sync(0xffffffffu, tc_pixel_done(ps))) {
         counted = true;
-        if (lane == 0) atomicAdd(&ctl.done_warps, 1);
+        if (lane == 0) {
+          // this warp votes "skip" for every batch after i
+          atomicMax(&ctl.skip_from, i + 1);
+          __threadfence_block();
+          atomicAdd(&ctl.done_warps, 1);
+        }
       }
     }
-    const float T = ps.T;
-    const int last = ps.last;
-    ctl.Tfin[tid] = T;
+    ctl.Tfin[tid] = ps.T;
     if (inside && ch0 == 0) {
       const size_t pix = (size_t)pyi * W + pxi;
-      alphas[pix] = 1.f - T;
-      last_ids[pix] = last;
+      alphas[pix] = 1.f - ps.T;
+      last_ids[pix] = ps.last;
     }
     // every MMA issued has completed once the last batch's commit has arrived
     if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
   } else if (warp < 8) {
-    // ======================= producer warps ========================================================
-    // Software pipeline per batch: (1) finish the pending scan round if the queue is short,
-    // (2) publish the batch list, (3) issue the feature-row loads, (4) issue the NEXT scan round's
-    // geometry loads, (5) split + store the feature rows, (6) signal the stage full.
-    const int p = tid - 128, pw = warp - 4;
-    const float hx0 = (float)x0 + 0.5f, hy0 = (float)y0 + 0.5f;
-    int scan = s, qtail = 0, qhead = 0;
-    // pending scan round (loads in flight): candidate idx = pend_scan + p
-    bool pending = false;
-    int pend_idx = 0, pend_gid = 0;
-    float4 pa0 = make_float4(0.f, 0.f, 0.f, 0.f), pa1 = pa0;
-    int nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
-
-    auto issue_scan = [&]() {
-      pend_idx = scan + p;
-      pend_gid = nxt_gid;
-      if (pend_gid >= 0) {
-        pa0 = __ldg(geom + pend_gid * 2);
-        pa1 = __ldg(geom + pend_gid * 2 + 1);
-      }
-      scan += 128;
-      nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
-      pending = true;
-    };
-    auto finish_scan = [&]() {
-      const unsigned mask = (pend_gid >= 0) ? tc_block_mask(pa0, pa1, hx0, hy0) : 0u;
-      const bool keep = mask != 0u;
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (lane == 0) ctl.wcnt[pw] = __popc(bal);
-      named_bar_sync(1, 128);
-      int basec = qtail, total = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = ctl.wcnt[k];
-        if (k < pw) basec += c;
-        total += c;
-      }
-      if (keep) {
-        const int slot = (basec + __popc(bal & ((1u << lane) - 1u))) & (RING - 1);
-        rg0[slot] = pa0;
-        rg1[slot] = make_float4(pa1.x, pa1.y, __int_as_float(pend_idx), __uint_as_float(mask));
-        rgid[slot] = pend_gid;
-      }
-      qtail += total;
-      pending = false;
-      named_bar_sync(1, 128);
-    };
-
-    if (scan < e) issue_scan();
+    // ======================= scanner warps =========================================================
+    const int p = tid - 128;
+    TcScanner sc;
+    sc.init(geom, ids, s, e, (float)x0 + 0.5f, (float)y0 + 0.5f, rg0, rg1, rgid, ctl.wcnt, p);
+    if (sc.scan < e) sc.issue();
     for (int i = 0;; ++i) {
       const int st = i & 1;
+      if (warp == 4) TC_STAMP(3, i + 1, 0);
       // uniform stop decision: the pixel warps have all terminated
-      if (warp == 4) TC_STAMP(1, i, 0);
       const int dw = *reinterpret_cast<volatile int *>(&ctl.done_warps);
       const bool stop_all = named_bar_or(1, 128, dw == 4);
-      while (!stop_all && (qtail - qhead) < KB && (pending || scan < e)) {
-        if (!pending) issue_scan();
-        finish_scan();
+      while (!stop_all && sc.queued() < KB && sc.more()) {
+        if (!sc.pending) sc.issue();
+        sc.finish();
       }
-      if (warp == 4) TC_STAMP(1, i, 1);
-      const int nb = stop_all ? 0 : min(KB, qtail - qhead);
+      if (warp == 4) TC_STAMP(3, i + 1, 1);
+      const int nb = stop_all ? 0 : min(KB, sc.queued());
+      // the next round's loads fly while this thread waits for the stage
+      if (!sc.pending && nb > 0 && (sc.queued() - nb) < KB && sc.scan < e) sc.issue();
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
-      if (warp == 4) TC_STAMP(1, i, 2);
-      if (p == 0) {
-        ctl.gcount[st] = nb;
-        ctl.gbase[st] = qhead & (RING - 1);
-      }
+      if (p == 0) ctl.gcount[st] = nb;
       if (p < KB) {
         TcRec r = tc_null_rec();
+        int gid = -1;
         if (p < nb) {
-          const int slot = (qhead + p) & (RING - 1);
+          const int slot = (sc.qhead + p) & (RING - 1);
           r = tc_make_rec(rg0[slot], rg1[slot]);
+          gid = rgid[slot];
         }
         ctl.rec0[st][p] = r.q0;
         ctl.rec1[st][p] = r.q1;
+        ctl.gid[st][p] = gid;
       }
       mbar_arrive(&ctl.list[st]);
+      if (warp == 4) TC_STAMP(3, i + 1, 2);
       if (nb == 0) break;
-      // gather + split the feature rows of this batch: warp pw owns rows [8 pw, 8 pw + 8)
+      sc.qhead += nb;
+    }
+  } else if (warp < 12) {
+    // ======================= converter warps =======================================================
+    // warp cw owns batch rows [8 cw, 8 cw + 8); lane owns channels [8 lane, 8 lane + 8).
+    const int cw = warp - 8;
+    const int n0 = lane * 8;
+    const bool chan_ok = n0 < nch;
+    const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
+    const float *cbase = colors + ch0 + n0;
+    float4 v[4][2];
+
+    auto header = [&](int i, int &nb, bool &skipb) {
+      const int st = i & 1;
+      mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
+      nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+      const int dw = *reinterpret_cast<volatile int *>(&ctl.done_warps);
+      const int sf = *reinterpret_cast<volatile int *>(&ctl.skip_from);
+      skipb = (dw == 4) && (i >= sf);               // all four pixel warps vote skip for batch i
+    };
+    auto load_row = [&](int i, int nb, bool skipb, int row, float4 (&dst)[2]) {
+      dst[0] = dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nb && chan_ok && !skipb) {
+        const int gid = ctl.gid[i & 1][row];
+        const float4 *src = reinterpret_cast<const float4 *>(cbase + (size_t)gid * D);
+        dst[0] = __ldg(src);
+        dst[1] = __ldg(src + 1);
+      }
+    };
+    auto store_row = [&](unsigned char *bhi, unsigned char *blo, int row, const float4 (&src)[2]) {
+      uint4 h, l;
+      split_pack2(src[0].x, src[0].y, h.x, l.x);
+      split_pack2(src[0].z, src[0].w, h.y, l.y);
+      split_pack2(src[1].x, src[1].y, h.z, l.z);
+      split_pack2(src[1].z, src[1].w, h.w, l.w);
+      const uint32_t off = (uint32_t)(row >> 3) * 1024u +
+                           sw128((uint32_t)(row & 7) * 128u + (coff & 127u)) + (coff & ~127u);
+      *reinterpret_cast<uint4 *>(bhi + off) = h;
+      *reinterpret_cast<uint4 *>(blo + off) = l;
+    };
+
+    int nb;
+    bool skipb;
+    header(0, nb, skipb);
+    if (nb > 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) load_row(0, nb, skipb, cw * 8 + j, v[j]);
+    }
+    for (int i = 0;; ++i) {
+      if (nb == 0) break;
+      const int st = i & 1;
+      if (warp == 8) TC_STAMP(1, i, 0);
       unsigned char *bhi = sB + (st * 2 + 0) * L::BPART;
       unsigned char *blo = sB + (st * 2 + 1) * L::BPART;
-      const int n0 = lane * 8;
       const int nbr = (nb + 15) & ~15;               // rows the MMAs will read
-      const bool chan_ok = n0 < nch;
-      const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
-      float4 v[8][2];
+      const bool do_store = chan_ok && !skipb;
+      if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+      if (warp == 8) TC_STAMP(1, i, 2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kk = pw * 8 + j;
-        v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kk < nb && chan_ok) {
-          const int gid = rgid[(qhead + kk) & (RING - 1)];
-          const float4 *src = reinterpret_cast<const float4 *>(colors + (size_t)gid * D + ch0 + n0);
-          v[j][0] = __ldg(src);
-          v[j][1] = __ldg(src + 1);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int row = cw * 8 + j;
+        if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
+        load_row(i, nb, skipb, row + 4, v[j]);
       }
-      if (warp == 4) TC_STAMP(1, i, 3);
-      // overlap the next scan round's geometry loads with the feature-row loads
-      if (!pending && (qtail - qhead - nb) < KB && scan < e) issue_scan();
-      if (chan_ok) {
+      if (warp == 8) TC_STAMP(1, i, 3);
+      int nb2;
+      bool skip2;
+      header(i + 1, nb2, skip2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kk = pw * 8 + j;
-          if (kk < nbr) {
-            uint4 h, l;
-            split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
-            split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
-            split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
-            split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
-            const uint32_t off = (uint32_t)(kk >> 3) * 1024u +
-                                 sw128((uint32_t)(kk & 7) * 128u + (coff & 127u)) + (coff & ~127u);
-            *reinterpret_cast<uint4 *>(bhi + off) = h;
-            *reinterpret_cast<uint4 *>(blo + off) = l;
-          }
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int row = cw * 8 + 4 + j;
+        if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
+        if (nb2 > 0) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
       }
       fence_async_smem();
       mbar_arrive(&ctl.full[st]);
-      if (warp == 4) TC_STAMP(1, i, 4);
-      qhead += nb;
+      if (warp == 8) TC_STAMP(1, i, 4);
+      nb = nb2;
+      skipb = skip2;
     }
   } else {
     // ======================= MMA issuer ============================================================
@@ -345,13 +345,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   __syncthreads();
   tc_fence_after();
   if (warp == 0) TC_STAMP(3, 0, 2);
-  if (warp < 8) {
+  if (warp < 12) {
     const bool any = ctl.any_mma != 0;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, third = warp >> 2;
     float *stg = reinterpret_cast<float *>(sm + warp * 4096);
     const int nchunk = (nch + 31) >> 5;
     const float Tp = ctl.Tfin[q * 32 + lane];
-    for (int cidx = half; cidx < nchunk; cidx += 2) {
+    for (int cidx = third; cidx < nchunk; cidx += 3) {
       const int c0 = cidx * 32;
       uint32_t r[32];
       if (any) {
@@ -387,7 +387,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   if (warp == 0) TC_STAMP(3, 0, 3);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<L::TCOLS>(tb);
+  if (warp == 12) tmem_dealloc<L::TCOLS>(tb);
 }
 
 template <int NATOM>

@@ -72,14 +72,26 @@ __device__ __forceinline__ float tc_ex2(float x) {
 
 struct TcPixel {
   float px, py;   // pixel centre
-  float T;        // transmittance in front of the next Gaussian
+  float P;        // running product of (1 - alpha); the pixel is finished once P <= 1e-4 (an
+                  // outside-image pixel starts at 0).  P keeps shrinking after the stop, which is
+                  // what zeroes every later weight without a sequential select.
+  float T;        // transmittance in front of the next Gaussian, frozen at the stop (A.5: the
+                  // stopping Gaussian does not contribute and does not update T)
   int last;       // list index of the last contributor
-  bool done;      // early-stopped (T' <= 1e-4) or outside the image
 };
+__device__ __forceinline__ void tc_pixel_init(TcPixel &st, float px, float py, bool inside) {
+  st.px = px; st.py = py; st.P = inside ? 1.f : 0.f; st.T = 1.f; st.last = 0;
+}
+__device__ __forceinline__ bool tc_pixel_done(const TcPixel &st) { return st.P <= GAGS_T_STOP; }
 
 // Weights of 8 consecutive Gaussians of the batch (records rec0[8], rec1[8] in shared memory) at
-// one pixel: 8 independent alpha evaluations, then the sequential transmittance chain written with
-// selects only.  Returns the bf16 hi / lo halves packed for one 16-byte chunk each.
+// one pixel.  The only loop-carried dependency is ONE fma per Gaussian (P' = P - alpha P): with
+// T_k = P_k while the pixel is alive and P non-increasing, "T_k (1 - alpha_k) <= 1e-4 stops the
+// pixel" is the monotone predicate P_{k+1} <= 1e-4, so
+//     w_k = (P_{k+1} > 1e-4) ? alpha_k P_k : 0
+// reproduces the sequential chain of Appendix A.5 bit for bit while every other operation (alpha
+// evaluation, products, selects, bf16 split) is independent across the 8 Gaussians.
+// Returns the bf16 hi / lo halves packed for one 16-byte chunk each.
 __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
                                             const float4 *__restrict__ rec1, TcPixel &st, uint4 &hi,
                                             uint4 &lo) {
@@ -97,20 +109,95 @@ __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
     a[k] = (q <= 0.f && al >= GAGS_ALPHA_MIN) ? al : 0.f;
     gi[k] = __float_as_int(r1.z);
   }
+  float P[9];
+  P[0] = st.P;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) P[k + 1] = fmaf(-a[k], P[k], P[k]);   // == P when alpha == 0
   float w[8];
+  float T = st.T;
+  int last = st.last;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float ae = st.done ? 0.f : a[k];
-    const float Tn = fmaf(-ae, st.T, st.T);               // T (1 - alpha); == T when alpha == 0
-    const bool stopnow = Tn <= GAGS_T_STOP;               // T > 1e-4 is invariant while !done
-    const float wk = stopnow ? 0.f : ae * st.T;
-    st.T = stopnow ? st.T : Tn;
-    st.done = st.done || stopnow;
-    st.last = (wk > 0.f) ? gi[k] : st.last;
-    w[k] = wk;
+    const bool alive = P[k + 1] > GAGS_T_STOP;
+    w[k] = alive ? a[k] * P[k] : 0.f;
+    T = alive ? P[k + 1] : T;
+    last = (w[k] > 0.f) ? gi[k] : last;
   }
+  st.P = P[8];
+  st.T = T;
+  st.last = last;
   split_pack2(w[0], w[1], hi.x, lo.x);
   split_pack2(w[2], w[3], hi.y, lo.y);
   split_pack2(w[4], w[5], hi.z, lo.z);
   split_pack2(w[6], w[7], hi.w, lo.w);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Scanner: per-thread state of the 128-thread warp group that walks a tile's depth-sorted list 128
+// entries at a time, culls every Gaussian whose alpha >= 1/255 bounding box misses the half tile
+// (exact: such a Gaussian contributes to no pixel of it) and appends the survivors, in list order,
+// to a ring in shared memory.  One round = ids load (prefetched a round ahead) -> geometry gather
+// -> cull -> warp ballots + 4-counter prefix -> ring insert.  `issue` starts a round's loads,
+// `finish` consumes them, so a caller can put other work between the two.
+// Uses named barrier 1 (128 threads).
+// ------------------------------------------------------------------------------------------------
+struct TcScanner {
+  const float4 *geom;
+  const int *ids;
+  float4 *rg0, *rg1;
+  int *rgid, *wcnt;
+  float hx0, hy0;
+  int e, p, pw, lane;
+  int scan, qtail, qhead;
+  bool pending;
+  int pend_idx, pend_gid, nxt_gid;
+  float4 pa0, pa1;
+
+  __device__ __forceinline__ void init(const float4 *geom_, const int *ids_, int s, int e_, float hx0_,
+                                       float hy0_, float4 *rg0_, float4 *rg1_, int *rgid_,
+                                       int *wcnt_, int p_) {
+    geom = geom_; ids = ids_; e = e_; hx0 = hx0_; hy0 = hy0_;
+    rg0 = rg0_; rg1 = rg1_; rgid = rgid_; wcnt = wcnt_;
+    p = p_; pw = p_ >> 5; lane = p_ & 31;
+    scan = s; qtail = 0; qhead = 0; pending = false;
+    pend_idx = 0; pend_gid = -1;
+    pa0 = make_float4(0.f, 0.f, 0.f, 0.f); pa1 = pa0;
+    nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
+  }
+  __device__ __forceinline__ bool more() const { return pending || scan < e; }
+  __device__ __forceinline__ int queued() const { return qtail - qhead; }
+  __device__ __forceinline__ void issue() {
+    pend_idx = scan + p;
+    pend_gid = nxt_gid;
+    if (pend_gid >= 0) {
+      pa0 = __ldg(geom + pend_gid * 2);
+      pa1 = __ldg(geom + pend_gid * 2 + 1);
+    }
+    scan += 128;
+    nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
+    pending = true;
+  }
+  __device__ __forceinline__ void finish() {
+    const unsigned mask = (pend_gid >= 0) ? tc_block_mask(pa0, pa1, hx0, hy0) : 0u;
+    const bool keep = mask != 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wcnt[pw] = __popc(bal);
+    named_bar_sync(1, 128);
+    int basec = qtail, total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = wcnt[k];
+      if (k < pw) basec += c;
+      total += c;
+    }
+    if (keep) {
+      const int slot = (basec + __popc(bal & ((1u << lane) - 1u))) & (TC_RING - 1);
+      rg0[slot] = pa0;
+      rg1[slot] = make_float4(pa1.x, pa1.y, __int_as_float(pend_idx), __uint_as_float(mask));
+      rgid[slot] = pend_gid;
+    }
+    qtail += total;
+    pending = false;
+    named_bar_sync(1, 128);
+  }
+};

@@ -8,19 +8,22 @@
 #include "common.cuh"
 
 // ---- mbarrier helpers with a bounded spin (a protocol bug traps instead of hanging the GPU) ----
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or the
+// hint (ns) expires, instead of re-issuing the probe every few cycles next to the working warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
-  for (int i = 0; i < (1 << 22); ++i)
+#pragma unroll 1
+  for (int i = 0; i < (1 << 20); ++i)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }

@@ -20,6 +20,16 @@ def frac_bad(a, b, rtol=1e-4):
     return float(((a - b).abs() > rtol * scale).double().mean())
 
 
+def bad_pixels(a, b, rtol=1e-4):
+    """number of pixels ([..., D] rows) with any channel off by more than rtol * tensor scale.
+    Two implementations that round alpha differently may disagree on whether a Gaussian passes the
+    alpha >= 1/255 or T <= 1e-4 threshold at an isolated pixel; the tests bound how many."""
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = max(float(b.abs().max()), 1e-12)
+    bad = ((a - b).abs() > rtol * scale).reshape(-1, a.shape[-1]).any(dim=-1)
+    return int(bad.sum())
+
+
 def identity_cam(width, height, fov_deg=60.0):
     fovx = math.radians(fov_deg)
     fx = width / (2 * math.tan(fovx / 2))

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import gags_oracle as O
-from tests.helpers import frac_bad, front_scene, rel_err
+from tests.helpers import bad_pixels, frac_bad, front_scene, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -129,8 +129,8 @@ def test_blend_forward_matches_oracle(D):
     out, alphas, last = R._Blend.apply(st["means2d"], st["conics"], st["opac"], sc["colors"].cuda(),
                                        bg.cuda(), st["geom"], st["offsets"], st["flatten_ids"], W, H)
     assert out.shape == (H, W, D)
-    assert frac_bad(out, ref, RTOL) < 1e-4 and rel_err(out, ref) < 5e-3
-    assert frac_bad(alphas, ref_a, RTOL) < 1e-4
+    assert bad_pixels(out, ref, RTOL) <= 3 and rel_err(out, ref) < 5e-3
+    assert bad_pixels(alphas.reshape(-1, 1), ref_a.reshape(-1, 1), RTOL) <= 3
     assert float((last.cpu() != ref_last).double().mean()) < 1e-3
 
 
@@ -170,8 +170,9 @@ def test_tensor_core_forward_matches_simt_and_oracle(D, n, opac_lo, blend_impl):
     assert rel_err(a_t, a_s) < 1e-5 and float((l_s != l_t).double().mean()) < 1e-3
     # two implementations, different rounding: a Gaussian sitting exactly on the alpha = 1/255 or
     # T = 1e-4 threshold may flip at isolated pixels, so bound the FRACTION of deviating values
-    assert frac_bad(tc, simt, 3e-5) < 1e-4 and rel_err(tc, simt) < 5e-3
-    assert frac_bad(tc, ref, RTOL) < 1e-4 and rel_err(tc, ref) < 5e-3
+    # (112 x 72 = 8064 pixels: at most 3 may differ)
+    assert bad_pixels(tc, simt, 3e-5) <= 3 and rel_err(tc, simt) < 5e-3
+    assert bad_pixels(tc, ref, RTOL) <= 3 and rel_err(tc, ref) < 5e-3
     assert float((l_t.cpu() != ref_last).double().mean()) < 1e-3
 
 
@@ -189,7 +190,7 @@ def test_wide_blend_equals_channelwise_narrow():
                                      col[:, c0:c0 + 32].contiguous(), None, st["geom"],
                                      st["offsets"], st["flatten_ids"], W, H)
         # bf16 hi/lo split vs fp32 FMA; isolated threshold flips allowed (see above)
-        assert frac_bad(wide[..., c0:c0 + 32], part, 3e-5) < 1e-4
+        assert bad_pixels(wide[..., c0:c0 + 32], part, 3e-5) <= 3
         assert rel_err(wide[..., c0:c0 + 32], part) < 5e-3
         assert rel_err(a1, a2) < 1e-5
 

@@ -28,18 +28,20 @@ _C.lib.gags_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
 rc = _C.lib.gags_debug_timeline(buf, n)
 assert rc == 0, rc
 t = torch.tensor(list(buf), dtype=torch.int64).reshape(8, 4, 64, 8)
-names = {0: ["top", "list_ok", "free_ok", "stored"], 1: ["top", "scanned", "free_ok", "loads_issued", "stored"],
-         2: ["wait_full", "full_ok", "committed"]}
+names = {0: ["top", "list_ok", None, "stored"], 1: ["top", None, "free_ok", "half", "stored"],
+         2: ["wait_full", "full_ok", "committed"], 3: ["top", "scanned", "published"]}
+print("columns: scan(top scanned published) | conv(top free_ok half stored) | pix(top list_ok stored) | mma(wait_full full_ok committed)")
 for slot in range(8):
     t0 = int(t[slot, 3, 0, 0])
     if t0 == 0:
         continue
     print(f"=== CTA slot {slot}: epilogue-sync at +{int(t[slot,3,0,1])-t0}, after-sync +{int(t[slot,3,0,2])-t0}, end +{int(t[slot,3,0,3])-t0}")
-    for b in range(64):
-        if t[slot, 0, b, 0] == 0 and t[slot, 1, b, 0] == 0:
+    for b in range(62):
+        if t[slot, 0, b, 0] == 0 and t[slot, 3, b + 1, 0] == 0:
             break
         line = f" b{b:2d} "
-        for role, tag in ((1, "prod"), (0, "pix"), (2, "mma")):
-            vals = [int(x) - t0 if x else -1 for x in t[slot, role, b, :len(names[role])]]
+        for role, tag, bb in ((3, "scan", b + 1), (1, "conv", b), (0, "pix", b), (2, "mma", b)):
+            vals = [int(t[slot, role, bb, k]) - t0 if t[slot, role, bb, k] else -1
+                    for k, nm in enumerate(names[role]) if nm is not None]
             line += f"| {tag} " + " ".join(f"{v:6d}" for v in vals) + " "
         print(line)
