@@ -57,6 +57,11 @@ SIGNATURES = {
     "gags_tile_offsets": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "gags_blend_fwd": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "gags_blend_bwd_features": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "gags_blend_cache_supported": (C.c_int, [_i32]),
+    "gags_blend_cache_slots": (_i64, [_i64, _i32]),
+    "gags_blend_fwd_cached": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                                        _p, _p]),
+    "gags_blend_bwd_features_cached": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gags_blend_bwd_full": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                       _p, _p, _p]),
     "gags_l1_loss_fused": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p]),

@@ -78,14 +78,14 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
 
   if (tid == 0) {
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&ctl.list[k], 128);
-      mbar_init(&ctl.full[k], 128);
+      mbar_init(&ctl.list[k], 4);
+      mbar_init(&ctl.full[k], 4);
       mbar_init(&ctl.free_[k], 1);
       mbar_init(&ctl.accfull[k], 1);
-      mbar_init(&ctl.accfree[k], 128);
+      mbar_init(&ctl.accfree[k], 4);
       ctl.gcount[k] = 0; ctl.gbase[k] = 0; ctl.skip[k] = 0;
     }
-    mbar_init(&ctl.vfull, 128);
+    mbar_init(&ctl.vfull, 4);
     ctl.done_warps = 0;
     ctl.term = -1;
     mbar_fence_init();
@@ -130,7 +130,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
         }
       }
       fence_async_smem();
-      mbar_arrive(&ctl.full[st]);
+      mbar_arrive_warp(&ctl.full[st]);
       if (!counted && __all_sync(0xffffffffu, tc_pixel_done(ps))) {
         counted = true;
         if (lane == 0) atomicAdd(&ctl.done_warps, 1);
@@ -209,7 +209,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
         ctl.rec0[st][p] = r.q0;
         ctl.rec1[st][p] = r.q1;
       }
-      mbar_arrive(&ctl.list[st]);
+      mbar_arrive_warp(&ctl.list[st]);
       if (nb == 0) break;
       qhead += nb;
     }
@@ -255,7 +255,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
         }
       }
       fence_async_smem();
-      mbar_arrive(&ctl.vfull);
+      mbar_arrive_warp(&ctl.vfull);
     }
     float *stg = reinterpret_cast<float *>(sm + L::STG_OFF + q * 4096);
     for (int i = 0;; ++i) {
@@ -281,7 +281,7 @@ blend_bwd_tc(const float4 *__restrict__ geom, int D, int ch0, int nch, int W, in
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctl.accfree[buf]);
+      mbar_arrive_warp(&ctl.accfree[buf]);
       if (skipped) continue;
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {

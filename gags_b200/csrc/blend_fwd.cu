@@ -317,17 +317,21 @@ int launch_wide(const float *geom, const float *colors, int D, int ch0, const fl
 int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const float *background,
                       int32_t width, int32_t height, const int32_t *offsets,
                       const int32_t *flatten_ids, float *render, float *alphas, int32_t *last_ids,
+                      unsigned char *wcache, int32_t *wmeta, int32_t *wlist, int32_t *wcount,
                       cudaStream_t st);
 extern int g_gags_blend_impl;
 
-extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
-                              const float *background, int32_t width, int32_t height,
-                              const int32_t *offsets, const int32_t *flatten_ids, float *render,
-                              float *alphas, int32_t *last_ids, void *stream) {
+static int blend_fwd_impl(const float *geom, const float *colors, int32_t D, const float *background,
+                          int32_t width, int32_t height, const int32_t *offsets,
+                          const int32_t *flatten_ids, float *render, float *alphas,
+                          int32_t *last_ids, unsigned char *wcache, int32_t *wmeta, int32_t *wlist,
+                          int32_t *wcount, void *stream) {
   if (!geom || !colors || !offsets || !render || !alphas || !last_ids) return GAGS_EINVAL;
   if (D < 1 || width <= 0 || height <= 0) return GAGS_EINVAL;
   if (!gags_aligned16(geom)) return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = D > 32 && D % 16 == 0 && g_gags_blend_impl != 1;
+  if (wcache && !tc) return GAGS_EINVAL;
   if (D <= 32) {
     if (D <= 4) return launch_narrow<4>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
     if (D <= 8) return launch_narrow<8>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
@@ -337,9 +341,9 @@ extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
   if (D % 4 != 0) return GAGS_EINVAL;
   if (!gags_aligned16(colors) || !gags_aligned16(render) || (background && !gags_aligned16(background)))
     return GAGS_EALIGN;
-  if (g_gags_blend_impl != 1 && D % 16 == 0)
+  if (tc)
     return gags_blend_fwd_tc(geom, colors, D, background, width, height, offsets, flatten_ids,
-                             render, alphas, last_ids, st);
+                             render, alphas, last_ids, wcache, wmeta, wlist, wcount, st);
   if (g_gags_blend_impl == 2) return GAGS_EINVAL;
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
@@ -354,4 +358,35 @@ extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
+                              const float *background, int32_t width, int32_t height,
+                              const int32_t *offsets, const int32_t *flatten_ids, float *render,
+                              float *alphas, int32_t *last_ids, void *stream) {
+  return blend_fwd_impl(geom, colors, D, background, width, height, offsets, flatten_ids, render,
+                        alphas, last_ids, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int gags_blend_cache_supported(int32_t D) {
+  return (D > 32 && D % 16 == 0 && g_gags_blend_impl != 1) ? 1 : 0;
+}
+
+extern "C" int64_t gags_blend_cache_slots(int64_t n_isects, int32_t n_tiles) {
+  // half tile (t, h) owns slots [2 b(t) + h span(t), + span(t)),  b(t) = (offsets[t] >> 5) + t,
+  // span(t) = b(t+1) - b(t) >= ceil(len(t) / 32): a scan-free upper bound on its batch count
+  return 2 * ((n_isects >> 5) + (int64_t)n_tiles) + 2;
+}
+
+extern "C" int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
+                                     const float *background, int32_t width, int32_t height,
+                                     const int32_t *offsets, const int32_t *flatten_ids,
+                                     float *render, float *alphas, int32_t *last_ids,
+                                     void *wcache, int32_t *wmeta, int32_t *wlist, int32_t *wcount,
+                                     void *stream) {
+  if (!wcache || !wmeta || !wlist || !wcount) return GAGS_EINVAL;
+  if (!gags_aligned16(wcache)) return GAGS_EALIGN;
+  return blend_fwd_impl(geom, colors, D, background, width, height, offsets, flatten_ids, render,
+                        alphas, last_ids, reinterpret_cast<unsigned char *>(wcache), wmeta, wlist,
+                        wcount, stream);
 }

@@ -9,7 +9,7 @@
 // products hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (measured 4e-6 relative,
 // tools/umma_probe.cu).
 //
-// One CTA = one half tile, 13 warps, warp-specialised, two smem stages of 32 Gaussians:
+// One CTA = one half tile, 14 warps, warp-specialised, two smem stages of 32 Gaussians:
 //   warps 4-7   scanner: walks the tile list 128 entries at a time, culls every Gaussian whose
 //               alpha >= 1/255 ellipse misses the half tile (exact), keeps the survivors in a ring
 //               and publishes one batch (32 blend records + Gaussian ids) per stage.
@@ -19,6 +19,8 @@
 //               bf16 hi/lo in registers and store them in the MN-major SWIZZLE_128B layout.
 //   warps 0-3   one thread per pixel: evaluate alpha, transmittance product, write the weight row
 //               [hi(32) | lo(32)] (128 B, K-major SWIZZLE_128B).
+//   warp 13     (training) one thread stores each blended batch's weight tile to the cache with a
+//               bulk async copy for the cached backward (blend_bwd_cached.cu).
 //   warp 12     one thread issues tcgen05.mma (M=128, N=D, K=16) x 3 products x 2 k-steps per batch;
 //               tcgen05.commit frees the stage.
 // Epilogue (warps 0-11): tcgen05.ld -> + T*background -> per-warp transpose in smem -> 128-B
@@ -48,7 +50,7 @@ namespace {
 
 constexpr int KB = TC_KB;
 constexpr int RING = TC_RING;
-constexpr int TC_THREADS = 416;
+constexpr int TC_THREADS = 448;   // 13 role warps + the weight-tile store warp
 
 struct TcCtl {
   uint64_t list[2], full[2], free_[2];
@@ -83,7 +85,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, int D, int ch0,
              int nch, const float *__restrict__ bg, int W, int H, int tile_w,
              const int *__restrict__ offsets, const int *__restrict__ ids,
-             float *__restrict__ render, float *__restrict__ alphas, int *__restrict__ last_ids) {
+             float *__restrict__ render, float *__restrict__ alphas, int *__restrict__ last_ids,
+             unsigned char *__restrict__ wcache, int *__restrict__ wmeta, int *__restrict__ wlist,
+             int *__restrict__ wcount) {
   using L = TcLayout<NATOM>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -98,6 +102,11 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   const int tile = (blockIdx.y >> 1) * tile_w + blockIdx.x;
   const int x0 = blockIdx.x * GAGS_TILE, y0 = blockIdx.y * 8;
   const int s = offsets[tile], e = offsets[tile + 1];
+  // weight-tile cache (training only): batch i of this half tile lives in slot hbase + i, see
+  // gags_blend_cache_slots() for the closed-form, scan-free slot bound
+  const bool cache = wcache != nullptr;
+  const int cbase = (s >> 5) + tile;
+  const int hbase = 2 * cbase + (int)(blockIdx.y & 1) * ((e >> 5) + tile + 1 - cbase);
 #ifdef GAGS_TC_TIMING
   // 8 sampled CTAs spread over the grid
   int dbg_slot = -1;
@@ -110,9 +119,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 
   if (tid == 0) {
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&ctl.list[k], 128);
-      mbar_init(&ctl.full[k], 256);
-      mbar_init(&ctl.free_[k], 1);
+      mbar_init(&ctl.list[k], 4);                  // scanner warps
+      mbar_init(&ctl.full[k], 8);                  // pixel + converter warps
+      mbar_init(&ctl.free_[k], cache ? 2 : 1);     // MMA commit (+ the tile store has read the stage)
       ctl.gcount[k] = 0; ctl.skip[k] = 0;
     }
     ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0;
@@ -159,8 +168,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           *reinterpret_cast<uint4 *>(arow + sw128(rowoff + (c + 4) * 16)) = l;
         }
       }
+      if (warp == 0) TC_STAMP(0, i, 2);
       fence_async_smem();
-      mbar_arrive(&ctl.full[st]);
+      mbar_arrive_warp(&ctl.full[st]);
       if (warp == 0) TC_STAMP(0, i, 3);
       if (!counted && __all_sync(0xffffffffu, tc_pixel_done(ps))) {
         counted = true;
@@ -213,8 +223,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         ctl.rec0[st][p] = r.q0;
         ctl.rec1[st][p] = r.q1;
         ctl.gid[st][p] = gid;
+        if (cache && nb > 0) wmeta[(size_t)(hbase + i) * KB + p] = gid;
       }
-      mbar_arrive(&ctl.list[st]);
+      mbar_arrive_warp(&ctl.list[st]);
       if (warp == 4) TC_STAMP(3, i + 1, 2);
       if (nb == 0) break;
       sc.qhead += nb;
@@ -292,12 +303,12 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         if (nb2 > 0) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
       }
       fence_async_smem();
-      mbar_arrive(&ctl.full[st]);
+      mbar_arrive_warp(&ctl.full[st]);
       if (warp == 8) TC_STAMP(1, i, 4);
       nb = nb2;
       skipb = skip2;
     }
-  } else {
+  } else if (warp == 12) {
     // ======================= MMA issuer ============================================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(nch, false, true);
@@ -335,6 +346,38 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         TC_STAMP(2, i, 2);
       }
       ctl.any_mma = (int)acc;
+    }
+    __syncwarp();
+  } else {
+    // ======================= weight-tile store warp (training forward only) =========================
+    // One bulk async copy (TMA, shared -> global) per blended batch: the 16 KB tile leaves exactly
+    // as the MMA reads it.  The stage is handed back (second arrival on free_) once the copy has
+    // finished reading shared memory.
+    if (cache && lane == 0) {
+      int seen[2] = {0, 0};
+      int stored = 0;
+      for (int i = 0;; ++i) {
+        const int st = i & 1;
+        mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
+        const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+        if (nb == 0) break;
+        mbar_wait_bounded(&ctl.full[st], (i >> 1) & 1);
+        const int votes_now = *reinterpret_cast<volatile int *>(&ctl.skip[st]);
+        const int votes = votes_now - seen[st];
+        seen[st] = votes_now;
+        if (votes < 4) {
+          wlist[hbase + stored++] = i;                // batches the backward has to visit
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                           wcache + (size_t)(hbase + i) * 16384),
+                       "r"(smem_u32(sA + st * 16384)), "r"(16384u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        mbar_arrive(&ctl.free_[st]);
+      }
+      wcount[blockIdx.y * gridDim.x + blockIdx.x] = stored;
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
   }
@@ -393,7 +436,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 template <int NATOM>
 int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
               int H, const int *offsets, const int *ids, float *render, float *alphas,
-              int *last_ids, cudaStream_t st) {
+              int *last_ids, unsigned char *wcache, int *wmeta, int *wlist, int *wcount,
+              cudaStream_t st) {
   using L = TcLayout<NATOM>;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
@@ -406,27 +450,34 @@ int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, c
   }
   blend_fwd_tc<NATOM><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
       reinterpret_cast<const float4 *>(geom), colors, D, ch0, nch, bg, W, H, tw, offsets, ids,
-      render, alphas, last_ids);
+      render, alphas, last_ids, wcache, wmeta, wlist, wcount);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
 
-// Tensor-core wide forward: 32 < D, D % 16 == 0.  Channels are processed 256 per launch.
+// Tensor-core wide forward: 32 < D, D % 16 == 0.  Channels are processed 256 per launch.  When
+// `wcache` is non-NULL the first launch also saves every batch's weight tile (+ Gaussian ids) for
+// gags_blend_bwd_features_cached (blend_bwd_cached.cu).
 int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const float *background,
                       int32_t width, int32_t height, const int32_t *offsets,
                       const int32_t *flatten_ids, float *render, float *alphas, int32_t *last_ids,
+                      unsigned char *wcache, int32_t *wmeta, int32_t *wlist, int32_t *wcount,
                       cudaStream_t st) {
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
     const int natom = (nch + 63) / 64;
+    unsigned char *wc = ch0 == 0 ? wcache : nullptr;
     int rc;
+#define GAGS_TC_ARGS geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, \
+                     render, alphas, last_ids, wc, wmeta, wlist, wcount, st
     switch (natom) {
-      case 1: rc = launch_tc<1>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
-      case 2: rc = launch_tc<2>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
-      case 3: rc = launch_tc<3>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
-      default: rc = launch_tc<4>(geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st); break;
+      case 1: rc = launch_tc<1>(GAGS_TC_ARGS); break;
+      case 2: rc = launch_tc<2>(GAGS_TC_ARGS); break;
+      case 3: rc = launch_tc<3>(GAGS_TC_ARGS); break;
+      default: rc = launch_tc<4>(GAGS_TC_ARGS); break;
     }
+#undef GAGS_TC_ARGS
     if (rc != 0) return rc;
   }
   return 0;

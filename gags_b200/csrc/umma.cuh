@@ -28,6 +28,15 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
   __trap();
 }
 
+// One arrival per WARP (barrier counts are in warps): 32x fewer mbarrier events, which is what wakes
+// the NANOSLEEP.SYNCS of every waiting warp of the CTA.  __syncwarp orders the other lanes' shared-
+// memory writes (each lane issues its own fence.proxy.async first when the consumer is the async
+// proxy) before lane 0's releasing arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {

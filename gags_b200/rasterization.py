@@ -23,6 +23,38 @@ from . import _C
 
 TILE = 16
 
+# Keep the forward's blend-weight tiles for the feature backward (training with frozen geometry).
+# The parity tests switch it off to exercise the recomputing backward kernels as well.
+weight_cache = True
+
+# The cache is sized by a closed-form bound (2 x (n_isects / 32 + n_tiles) tiles of 16 KB, ~10 GB at
+# N = 2M / 1080p), of which a view touches ~15 %.  One grow-only buffer set per device is reused by
+# every view: a view's tiles are dead once its backward has run, and a second forward before that
+# backward (two live graphs) gets a fresh set instead.
+_cache_pool: Dict = {}
+
+
+class _CacheLease:
+    """Buffers of one forward; returns them to the pool when the autograd node dies."""
+
+    def __init__(self, dev, slots: int, n_half: int):
+        key = (dev.type, dev.index)
+        bufs = _cache_pool.pop(key, None)
+        if bufs is None or bufs[2].numel() < slots or bufs[3].numel() < n_half:
+            cap = int(slots * 1.25) + 1024
+            bufs = (torch.empty(cap * 16384, dtype=torch.uint8, device=dev),
+                    torch.empty(cap * 32, dtype=torch.int32, device=dev),
+                    torch.empty(cap, dtype=torch.int32, device=dev),
+                    torch.empty(max(n_half, 1), dtype=torch.int32, device=dev))
+        self.key, self.bufs = key, bufs
+
+    def __del__(self):
+        try:
+            if self.key not in _cache_pool:
+                _cache_pool[self.key] = self.bufs
+        except Exception:
+            pass
+
 # Optional per-stage timing hooks (used by bench.py for the roofline numbers): when `stage_events`
 # is a list, every stage boundary appends (name, torch.cuda.Event) recorded on the current stream.
 stage_events = None
@@ -235,12 +267,29 @@ class _Blend(torch.autograd.Function):
         render = torch.empty(height, width, D, dtype=torch.float32, device=dev)
         alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
         last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
-        _C.check(_C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height,
-                                       _C.ptr(offsets), _C.ptr(flatten_ids), _C.ptr(render),
-                                       _C.ptr(alphas), _C.ptr(last_ids), _C.stream_ptr()),
-                 "gags_blend_fwd")
+        # frozen geometry + trainable features (the shipped training loop): keep the blend-weight
+        # tiles of this forward so the backward is a streaming GEMM instead of a second tile walk
+        need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        cache = None
+        if (weight_cache and ctx.needs_input_grad[3] and not need_geo
+                and _C.lib.gags_blend_cache_supported(D)):
+            n_tiles = offsets.numel() - 1
+            slots = int(_C.lib.gags_blend_cache_slots(flatten_ids.numel(), n_tiles))
+            lease = _CacheLease(dev, slots, ((width + TILE - 1) // TILE) * ((height + 7) // 8))
+            cache = lease.bufs
+            _C.check(_C.lib.gags_blend_fwd_cached(
+                _C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height, _C.ptr(offsets),
+                _C.ptr(flatten_ids), _C.ptr(render), _C.ptr(alphas), _C.ptr(last_ids),
+                _C.ptr(cache[0]), _C.ptr(cache[1]), _C.ptr(cache[2]), _C.ptr(cache[3]),
+                _C.stream_ptr()), "gags_blend_fwd_cached")
+        else:
+            _C.check(_C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width,
+                                           height, _C.ptr(offsets), _C.ptr(flatten_ids),
+                                           _C.ptr(render), _C.ptr(alphas), _C.ptr(last_ids),
+                                           _C.stream_ptr()), "gags_blend_fwd")
         _C.count_launch((D + 255) // 256 if D > 32 else 1)
         ctx.dims = (width, height, D, N)
+        ctx.lease = lease if cache is not None else None
         ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
         ctx.mark_non_differentiable(last_ids)
         return render, alphas, last_ids
@@ -248,6 +297,7 @@ class _Blend(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alphas, _vl):
         colors, bg, geom, offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
+        cache = ctx.lease.bufs if ctx.lease is not None else None
         width, height, D, N = ctx.dims
         dev = colors.device
         need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
@@ -261,7 +311,13 @@ class _Blend(torch.autograd.Function):
         _mark("bwd_zero")
         v_m = v_c = v_o = v_bg = None
         if not need_geo:
-            if need_col:
+            if need_col and cache is not None:
+                _C.check(_C.lib.gags_blend_bwd_features_cached(
+                    D, width, height, _C.ptr(offsets), _C.ptr(cache[0]), _C.ptr(cache[1]),
+                    _C.ptr(cache[2]), _C.ptr(cache[3]), _C.ptr(v_render), _C.ptr(v_colors), st),
+                    "gags_blend_bwd_features_cached")
+                _C.count_launch((D + 255) // 256)
+            elif need_col:
                 # frozen geometry: the feature-only fast path
                 _C.check(_C.lib.gags_blend_bwd_features(_C.ptr(geom), D, width, height,
                                                         _C.ptr(offsets), _C.ptr(flatten_ids),

@@ -154,6 +154,27 @@ int gags_blend_bwd_features(const float *geom, int32_t D, int32_t width, int32_t
                             const int32_t *offsets, const int32_t *flatten_ids,
                             const float *v_render, float *v_colors, void *stream);
 
+/* K7 + K8a with a weight-tile cache (training with frozen geometry, D > 32, D % 16 == 0).
+ * gags_blend_fwd_cached is gags_blend_fwd that additionally saves, for every batch of 32 Gaussians
+ * it blends into a 16x8 half tile, the 128 x 32 blend-weight tile (bf16 hi/lo, 16 KB) and the 32
+ * Gaussian ids; gags_blend_bwd_features_cached then computes v_colors as a streaming tensor-core
+ * GEMM over those tiles instead of re-walking the tile lists (same result as
+ * gags_blend_bwd_features).  Caller-owned buffers, `slots = gags_blend_cache_slots(n_isects,
+ * n_tiles)`:  wcache[slots * 16384] bytes (16-B aligned), wmeta[slots * 32], wlist[slots],
+ * wcount[tile_w * ceil(height / 8)].  None needs initialising.                                 */
+int gags_blend_cache_supported(int32_t D);     /* 1 if the cached pair handles this D          */
+int64_t gags_blend_cache_slots(int64_t n_isects, int32_t n_tiles);
+int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
+                          const float *background, int32_t width, int32_t height,
+                          const int32_t *offsets, const int32_t *flatten_ids, float *render,
+                          float *alphas, int32_t *last_ids, void *wcache, int32_t *wmeta,
+                          int32_t *wlist, int32_t *wcount, void *stream);
+int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
+                                   const int32_t *offsets, const void *wcache,
+                                   const int32_t *wmeta, const int32_t *wlist,
+                                   const int32_t *wcount, const float *v_render, float *v_colors,
+                                   void *stream);
+
 /* K8b full backward (replaces rasterize_to_pixels_bwd; App. A.6).  Outputs must be
  * zero-initialised; v_colors may be NULL (skip), v_alphas may be NULL (= 0).  D <= 256.
  * Out: v_means2d[N,2] v_conics[N,3] v_opacities[N] v_colors[N,D]                              */

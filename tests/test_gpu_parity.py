@@ -230,16 +230,25 @@ def test_tensor_core_feature_backward_matches_simt_and_oracle(D, n, opac_lo, ble
     ref, _, _ = O.blend_fwd(m2d, con, cols, op, None, W, H, offs, ids)
     (ref * v_out.double()).sum().backward()
     grads = {}
-    for impl in (1, 2):
-        blend_impl(impl)
-        col_g = sc["colors"].cuda().requires_grad_(True)
-        out, _, _ = R._Blend.apply(st["means2d"], st["conics"], st["opac"], col_g, None, st["geom"],
-                                   st["offsets"], st["flatten_ids"], W, H)
-        (out * v_out.cuda()).sum().backward()
-        torch.cuda.synchronize()
-        grads[impl] = col_g.grad
-    assert frac_bad(grads[2], grads[1], 3e-5) < 1e-4 and rel_err(grads[2], grads[1]) < 5e-3
-    assert frac_bad(grads[2], cols.grad, RTOL) < 1e-4 and rel_err(grads[2], cols.grad) < 5e-3
+    # 1 = SIMT, 2 = tcgen05 recomputing the weights, 3 = tcgen05 streaming the cached forward tiles
+    try:
+        for impl in (1, 2, 3):
+            blend_impl(min(impl, 2))
+            R.weight_cache = impl == 3
+            col_g = sc["colors"].cuda().requires_grad_(True)
+            out, _, _ = R._Blend.apply(st["means2d"], st["conics"], st["opac"], col_g, None,
+                                       st["geom"], st["offsets"], st["flatten_ids"], W, H)
+            (out * v_out.cuda()).sum().backward()
+            torch.cuda.synchronize()
+            grads[impl] = col_g.grad
+    finally:
+        R.weight_cache = True
+    for impl in (2, 3):
+        assert frac_bad(grads[impl], grads[1], 3e-5) < 1e-4 and rel_err(grads[impl], grads[1]) < 5e-3
+        assert frac_bad(grads[impl], cols.grad, RTOL) < 1e-4
+        assert rel_err(grads[impl], cols.grad) < 5e-3
+    # same weights: the cached kernel adds the (tiny) Vlo x Wlo product and reduces in another order
+    assert rel_err(grads[3], grads[2]) < 1e-5
 
 
 @pytest.mark.parametrize("D", [3, 4, 16, 32, 64, 256])
