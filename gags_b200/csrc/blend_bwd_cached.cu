@@ -10,18 +10,18 @@
 // (128 pixel rows x [hi(32) | lo(32)] bf16, SWIZZLE_128B, 16 KB) plus the 32 Gaussian ids.  The
 // backward therefore recomputes nothing: it is a streaming GEMM per half tile,
 //        Dt[ch, g] = Vt[ch, 128 px] * Wt[128 px, g]
-// with A = Vt resident (the half tile of v_render split to bf16 hi/lo, MN-major SWIZZLE_128B) and
-// B = two cached tiles (64 Gaussians) per step landed by 1-D bulk async copies (UBLKCP).  Per k-step
-//        Vhi x [Whi|Wlo|Whi'|Wlo']  and  Vlo x [same]          (N = 128 each; a tcgen05.mma costs
-// ~69 cycles for any N <= 128 on B200 — tools/umma_rate.cu — so wide-N steps halve the MMA time of
-// 32-Gaussian steps), column g + column 32+g = (Vhi+Vlo)(Whi+Wlo).  Accumulators are double-
-// buffered in TMEM; the epilogue warps drain a step (tcgen05.ld -> add halves -> [32 g][128 ch] fp32
+// with A = Vt resident (128 channels of the half tile of v_render split to bf16 hi/lo, MN-major
+// SWIZZLE_128B) and B = one cached tile per step landed by a 1-D bulk async copy (UBLKCP).  Per
+// k-step  Vhi x [Whi|Wlo]  and  Vlo x [Whi|Wlo]  (N = 64 each), column g + column 32+g =
+// (Vhi+Vlo)(Whi+Wlo).  One CTA = half tile x 128 channels with a 64 KB A tile, so TWO CTAs share an
+// SM and one's v_render staging (pure HBM latency) hides behind the other's MMAs and reductions.
+// Accumulators are double-buffered in TMEM; the epilogue warps drain a step (tcgen05.ld -> add halves -> [32 g][128 ch] fp32
 // tile in smem -> ONE bulk async reduction per Gaussian row, cp.reduce.async.bulk .add.f32, 512 B
 // contiguous: the adds happen at L2 and the SM's LSU issues 32 instructions per tile instead of
 // 256 vector reds, which measured ~130 cycles each per SM) while the next step's MMAs run.
 //
-// Warps: 0-7 v_render staging then epilogue (two groups of four TMEM lane quarters), 8 bulk-copy
-// producer, 9 MMA issue.  One CTA per SM.
+// Warps: 0-3 v_render staging then epilogue (the four TMEM lane quarters), 4 bulk-copy producer,
+// 5 MMA issue.  Two CTAs per SM.
 //
 // Roofline: HBM — H*W*4D (v_render, once) + 16.1 KB per cached batch + N_contrib*4D*2 (reduction
 // target; the reductions resolve in L2).
@@ -43,25 +43,26 @@ extern "C" int gags_debug_timeline_bwd(long long *host_dst, int n) {
 
 namespace {
 
-constexpr int CB_THREADS = 320;   // warps 0-7 staging + epilogue, 8 bulk-copy producer, 9 MMA issue
+constexpr int CB_THREADS = 192;   // warps 0-3 staging + epilogue, 4 bulk-copy producer, 5 MMA issue
 
 struct CbCtl {
   uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull;
   uint32_t tmem_base;
-  uint32_t nzmask[2][4];      // per epilogue group and warp: Gaussians with a non-zero row
+  uint32_t nzmask[4];         // per epilogue warp: Gaussians with a non-zero row
 };
 
-template <int MB>
+// One CTA = one 16x8 half tile x one block of 128 channels; two CTAs per SM, so one CTA's v_render
+// staging (HBM latency) hides behind the other's MMAs and reductions.
 struct CbLayout {
-  static constexpr int VPART = MB * 32768;             // one bf16 part of the resident v_render tile
+  static constexpr int VPART = 32768;                  // one bf16 part (hi or lo): 128 px x 128 ch
   static constexpr int V_OFF = 0;
-  static constexpr int W_OFF = 2 * VPART;              // 2 stages x 2 tiles x 16 KB
-  static constexpr int STG_OFF = W_OFF + 65536;        // 2 epilogue groups x [32 g][128 ch] fp32
-  static constexpr int CTL_OFF = STG_OFF + 32768;
+  static constexpr int W_OFF = 2 * VPART;              // 2 stages x one 16 KB weight tile
+  static constexpr int STG_OFF = W_OFF + 32768;        // [16 g][128 ch] fp32
+  static constexpr int CTL_OFF = STG_OFF + 8192;
   static constexpr int BYTES = CTL_OFF + (int)sizeof(CbCtl) + 1024;
-  static constexpr int ACC = MB * 128;                 // accumulator columns of one step
-  static constexpr int TCOLS = 2 * ACC;                // 256 or 512
+  static constexpr int TCOLS = 128;                    // 2 accumulator buffers x [hi(32) | lo(32)]
 };
+static_assert(CbLayout::BYTES <= (233472 / 2 - 1024), "cached backward must fit twice per SM");
 
 // shared -> global bulk async REDUCTION (TMA, fp32 add performed at L2): one op per Gaussian row
 __device__ __forceinline__ void bulk_red_add_f32(float *gdst, const void *ssrc, uint32_t bytes) {
@@ -73,21 +74,24 @@ __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <int MB>
-__global__ void __launch_bounds__(CB_THREADS, 1)
-blend_bwd_cached(int D, int ch0, int nch, int W, int H, int tile_w,
+__global__ void __launch_bounds__(CB_THREADS, 2)
+blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
                  const int *__restrict__ offsets, const unsigned char *__restrict__ wcache,
                  const int *__restrict__ wmeta, const int *__restrict__ wlist,
                  const int *__restrict__ wcount, const float *__restrict__ v_render,
                  float *__restrict__ v_colors) {
-  using L = CbLayout<MB>;
-  const int nbat = wcount[blockIdx.y * gridDim.x + blockIdx.x];
+  using L = CbLayout;
+  // blockIdx.x = tile column * nblk + channel block: the CTAs sharing a half tile's weight tiles
+  // are neighbours in launch order (their second read of a tile is an L2 hit)
+  const int tx = blockIdx.x / nblk, cblk = blockIdx.x - tx * nblk;
+  const int nbat = wcount[blockIdx.y * tile_w + tx];
   if (nbat <= 0) return;
-  const int tile = (blockIdx.y >> 1) * tile_w + blockIdx.x;
+  const int tile = (blockIdx.y >> 1) * tile_w + tx;
   const int s = offsets[tile], e = offsets[tile + 1];
   const int cbase = (s >> 5) + tile;
   const int hbase = 2 * cbase + (int)(blockIdx.y & 1) * ((e >> 5) + tile + 1 - cbase);
-  const int nsteps = (nbat + 1) >> 1;
+  const int cfirst = ch0 + cblk * 128;               // first channel of this CTA
+  const int cvalid = min(128, nch - cblk * 128);     // channels of this block that exist (% 16 == 0)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -96,7 +100,7 @@ blend_bwd_cached(int D, int ch0, int nch, int W, int H, int tile_w,
   CbCtl &ctl = *reinterpret_cast<CbCtl *>(sm + L::CTL_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int x0 = blockIdx.x * GAGS_TILE, y0 = blockIdx.y * 8;
+  const int x0 = tx * GAGS_TILE, y0 = blockIdx.y * 8;
 #ifdef GAGS_TC_TIMING
   int dbg_slot = -1;
   {
@@ -111,179 +115,146 @@ blend_bwd_cached(int D, int ch0, int nch, int W, int H, int tile_w,
       mbar_init(&ctl.wfull[k], 1);
       mbar_init(&ctl.wfree[k], 1);
       mbar_init(&ctl.accfull[k], 1);
-      mbar_init(&ctl.accfree[k], 8);               // epilogue warps
+      mbar_init(&ctl.accfree[k], 4);               // epilogue warps
     }
-    mbar_init(&ctl.vfull, 8);
+    mbar_init(&ctl.vfull, 4);
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  if (warp == 5) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = ctl.tmem_base;
 
-  if (warp < 8) {
+  if (warp < 4) {
     // ======================= v_render staging, then epilogue =======================================
-    const int q = warp & 3;                         // TMEM lane quarter == warp % 4; pixel block
-    const int hgrp = warp >> 2;                     // staging: pixel rows 16 hgrp..; epilogue group
+    const int q = warp;                             // TMEM lane quarter == warp % 4; pixel block
     {
-      // the whole 128 KB half tile is in flight at once: 32 x 16-B loads per thread
-      const int n0 = lane * 8;
-      const bool lane_on = n0 < MB * 128;
-      const bool chan_ok = n0 < nch;
-      const uint32_t coff = (uint32_t)(n0 >> 7) * 32768u + (uint32_t)((n0 >> 6) & 1) * 16384u +
-                            (uint32_t)((n0 & 63) >> 3) * 16u;
+      // the whole 64 KB block is in flight at once: 32 x 16-B loads per thread.
+      // lane -> 4 channels at 4 lane (first 16-B load) and 64 + 4 lane... keep 32-B granules:
+      // lane l owns channels [8 (l & 15), +8) of pixel row 2 j + (l >> 4)
+      const int n0 = (lane & 15) * 8;
+      const bool chan_ok = n0 < cvalid;
+      const uint32_t coff = (uint32_t)((n0 >> 6) & 1) * 16384u + (uint32_t)((n0 & 63) >> 3) * 16u;
       unsigned char *vhi = sV, *vlo = sV + L::VPART;
       float4 v[16][2];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int ql = hgrp * 16 + j;               // pixel index inside this quarter's 8x4 block
+        const int ql = 2 * j + (lane >> 4);         // pixel index inside this quarter's 8x4 block
         const int xx = x0 + ((q & 1) << 3) + (ql & 7), yy = y0 + ((q >> 1) << 2) + (ql >> 3);
         v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (chan_ok && xx < W && yy < H) {
           const float4 *src = reinterpret_cast<const float4 *>(
-              v_render + ((size_t)yy * W + xx) * D + ch0 + n0);
+              v_render + ((size_t)yy * W + xx) * D + cfirst + n0);
           v[j][0] = ldg_nc4(src);
           v[j][1] = ldg_nc4(src + 1);
         }
       }
-      if (lane_on) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = q * 32 + hgrp * 16 + j;     // row of the K = 128 px dimension
-          uint4 h, l;
-          split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
-          split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
-          split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
-          split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
-          const uint32_t off = (uint32_t)(r >> 3) * 1024u +
-                               sw128((uint32_t)(r & 7) * 128u + (coff & 127u)) + (coff & ~127u);
-          *reinterpret_cast<uint4 *>(vhi + off) = h;
-          *reinterpret_cast<uint4 *>(vlo + off) = l;
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int r = q * 32 + 2 * j + (lane >> 4); // row of the K = 128 px dimension
+        uint4 h, l;
+        split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
+        split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
+        split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
+        split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
+        const uint32_t off = (uint32_t)(r >> 3) * 1024u +
+                             sw128((uint32_t)(r & 7) * 128u + (coff & 127u)) + (coff & ~127u);
+        *reinterpret_cast<uint4 *>(vhi + off) = h;
+        *reinterpret_cast<uint4 *>(vlo + off) = l;
       }
       fence_async_smem();
       mbar_arrive_warp(&ctl.vfull);
       if (warp == 0) CB_STAMP(3, 0, 1);
     }
-    // Epilogue: group hgrp (4 warps = 4 TMEM lane quarters = 128 channels) owns M-block hgrp when
-    // MB == 2, or tile hgrp of every step when MB == 1.  Per (M-block, tile): TMEM -> registers ->
-    // [32 g][128 ch] fp32 in shared memory -> one bulk async reduction (TMA add at L2) per Gaussian
-    // row, 512 B contiguous.
-    float *stg = reinterpret_cast<float *>(sm + L::STG_OFF + hgrp * 16384);
-    const int bar_id = 2 + hgrp;
-    const bool issuer = (warp & 3) == 0;
-    const int mb = MB == 2 ? hgrp : 0;
-    const int cvalid = min(128, nch - mb * 128);    // channels of this M-block that exist
-    for (int gi = 0; gi < nsteps; ++gi) {
+    // Epilogue: the four warps are the four TMEM lane quarters = 128 channels.  Per step: TMEM ->
+    // registers -> [16 g][128 ch] fp32 in shared memory (two passes) -> one bulk async reduction
+    // (TMA add at L2) per Gaussian row, 512 B contiguous.
+    float *stg = reinterpret_cast<float *>(sm + L::STG_OFF);
+    for (int gi = 0; gi < nbat; ++gi) {
       const int buf = gi & 1;
-      const int nt = min(2, nbat - 2 * gi);
-      // Gaussian row this lane reduces into (issuer warp): straight from the cached ids
-      int gid[2] = {-1, -1};
-      if (issuer) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-          if (t < nt) {
-            const int slot = hbase + __ldg(wlist + hbase + 2 * gi + t);
-            gid[t] = __ldg(wmeta + (size_t)slot * TC_KB + lane);
-          }
+      // Gaussian row this lane reduces into (warp 0 issues): straight from the cached ids
+      int gid = -1;
+      if (warp == 0) {
+        const int slot = hbase + __ldg(wlist + hbase + gi);
+        gid = __ldg(wmeta + (size_t)slot * TC_KB + lane);
       }
       if (warp == 0) CB_STAMP(0, gi, 0);
       mbar_wait_bounded(&ctl.accfull[buf], (gi >> 1) & 1);
       tc_fence_after();
       if (warp == 0) CB_STAMP(0, gi, 1);
-      float acc[2][32];
+      float acc[32];
+      {
+        uint32_t ra[32], rb[32];
+        const uint32_t ta = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
+        tmem_ld_32x32(ta, ra);
+        tmem_ld_32x32(ta + 32, rb);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const bool mine = MB == 2 ? (t < nt) : (t == hgrp && t < nt);
-        if (mine) {
-          uint32_t ra[32], rb[32];
-          const uint32_t ta = tb + ((uint32_t)(q * 32) << 16) +
-                              (uint32_t)(buf * L::ACC + mb * 128 + t * 64);
-          tmem_ld_32x32(ta, ra);
-          tmem_ld_32x32(ta + 32, rb);
-#pragma unroll
-          for (int k = 0; k < 32; ++k) acc[t][k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
-        }
+        for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
       }
       tc_fence_before();
       mbar_arrive_warp(&ctl.accfree[buf]);
       if (warp == 0) CB_STAMP(0, gi, 2);
+      // a survivor that reached no pixel of the half tile has an exactly-zero row: no reduction
+      // (fp32 reductions top out at ~2.95 TB/s chip-wide on B200 — tools/red_rate.cu — which makes
+      // them this kernel's floor, so every skipped row counts)
+      uint32_t nz = 0;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const bool mine = MB == 2 ? (t < nt) : (t == hgrp && t < nt);
-        if (mine) {                                  // uniform over the group
-          named_bar_sync(bar_id, 128);               // staging buffer free (issuer waited the reads)
-          // a survivor that reached no pixel of the half tile has an exactly-zero row: no reduction
-          // (fp32 reductions top out at ~2.95 TB/s chip-wide on B200 — tools/red_rate.cu — which
-          // makes them this kernel's floor, so every skipped row counts)
-          uint32_t nz = 0;
+      for (int g = 0; g < 32; ++g) nz |= __any_sync(0xffffffffu, acc[g] != 0.f) ? (1u << g) : 0u;
 #pragma unroll
-          for (int g = 0; g < 32; ++g) {
-            stg[g * 128 + q * 32 + lane] = acc[t][g];
-            nz |= __any_sync(0xffffffffu, acc[t][g] != 0.f) ? (1u << g) : 0u;
-          }
-          if (lane == 0) ctl.nzmask[hgrp][q] = nz;
-          fence_async_smem();
-          named_bar_sync(bar_id, 128);
-          if (issuer) {
-            const uint32_t any = ctl.nzmask[hgrp][0] | ctl.nzmask[hgrp][1] | ctl.nzmask[hgrp][2] |
-                                 ctl.nzmask[hgrp][3];
-            if (gid[t] >= 0 && cvalid > 0 && ((any >> lane) & 1u))
-              bulk_red_add_f32(v_colors + (size_t)gid[t] * D + ch0 + mb * 128, stg + lane * 128,
-                               (uint32_t)cvalid * 4u);
-            bulk_commit();
-            bulk_wait_read0();
-          }
+      for (int half = 0; half < 2; ++half) {
+        named_bar_sync(2, 128);                      // staging buffer free (issuer waited the reads)
+#pragma unroll
+        for (int g = 0; g < 16; ++g) stg[g * 128 + q * 32 + lane] = acc[half * 16 + g];
+        if (lane == 0) ctl.nzmask[q] = nz;
+        fence_async_smem();
+        named_bar_sync(2, 128);
+        if (warp == 0) {
+          const uint32_t any = ctl.nzmask[0] | ctl.nzmask[1] | ctl.nzmask[2] | ctl.nzmask[3];
+          const int g = lane - half * 16;            // lanes [16 half, 16 half + 16) issue
+          if (g >= 0 && g < 16 && gid >= 0 && cvalid > 0 && ((any >> lane) & 1u))
+            bulk_red_add_f32(v_colors + (size_t)gid * D + cfirst, stg + g * 128, (uint32_t)cvalid * 4u);
+          bulk_commit();
+          bulk_wait_read0();
         }
       }
       if (warp == 0) CB_STAMP(0, gi, 3);
     }
-  } else if (warp == 8) {
-    // ======================= bulk-copy producer: two cached weight tiles per step ===================
+  } else if (warp == 4) {
+    // ======================= bulk-copy producer: one cached weight tile per step ====================
     if (lane == 0) {
-      for (int gi = 0; gi < nsteps; ++gi) {
+      for (int gi = 0; gi < nbat; ++gi) {
         const int st = gi & 1;
-        const int nt = min(2, nbat - 2 * gi);
         if (gi >= 2) mbar_wait_bounded(&ctl.wfree[st], ((gi >> 1) - 1) & 1);
         CB_STAMP(1, gi, 0);
-        mbar_expect_tx(&ctl.wfull[st], (uint32_t)nt * 16384u);
-        for (int t = 0; t < nt; ++t) {
-          const int slot = hbase + __ldg(wlist + hbase + 2 * gi + t);
-          bulk_g2s(sW + st * 32768 + t * 16384, wcache + (size_t)slot * 16384, 16384u,
-                   &ctl.wfull[st]);
-        }
+        mbar_expect_tx(&ctl.wfull[st], 16384u);
+        const int slot = hbase + __ldg(wlist + hbase + gi);
+        bulk_g2s(sW + st * 16384, wcache + (size_t)slot * 16384, 16384u, &ctl.wfull[st]);
       }
     }
     __syncwarp();
   } else {
     // ======================= MMA issuer ============================================================
     if (lane == 0) {
-      const uint32_t idesc128 = umma_idesc_bf16(128, true, true);
-      const uint32_t idesc64 = umma_idesc_bf16(64, true, true);
+      const uint32_t idesc = umma_idesc_bf16(64, true, true);
       const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 16384, 1024);
-      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW), 16384, 1024);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW), 16, 1024);
       mbar_wait_bounded(&ctl.vfull, 0);
-      for (int gi = 0; gi < nsteps; ++gi) {
+      for (int gi = 0; gi < nbat; ++gi) {
         const int st = gi & 1, buf = gi & 1;
-        const int nt = min(2, nbat - 2 * gi);
         CB_STAMP(2, gi, 0);
         mbar_wait_bounded(&ctl.wfull[st], (gi >> 1) & 1);
         CB_STAMP(2, gi, 1);
         if (gi >= 2) mbar_wait_bounded(&ctl.accfree[buf], ((gi >> 1) - 1) & 1);
         tc_fence_after();
         CB_STAMP(2, gi, 2);
-        const uint32_t idesc = nt == 2 ? idesc128 : idesc64;
-#pragma unroll
-        for (int m = 0; m < MB; ++m) {
-          const uint32_t d = tb + (uint32_t)(buf * L::ACC + m * 128);
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ahi = v_desc0 + (uint64_t)((m * 32768 + ks * 2048) >> 4);
-            const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
-            const uint64_t bw = w_desc0 + (uint64_t)((st * 32768 + ks * 2048) >> 4);
-            umma_bf16_ss(d, ahi, bw, idesc, ks > 0 ? 1u : 0u);
-            umma_bf16_ss(d, alo, bw, idesc, 1u);
-          }
+        const uint32_t d = tb + (uint32_t)(buf * 64);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ahi = v_desc0 + (uint64_t)((ks * 2048) >> 4);
+          const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
+          const uint64_t bw = w_desc0 + (uint64_t)((st * 16384 + ks * 2048) >> 4);
+          umma_bf16_ss(d, ahi, bw, idesc, ks > 0 ? 1u : 0u);
+          umma_bf16_ss(d, alo, bw, idesc, 1u);
         }
         umma_commit(&ctl.wfree[st]);
         umma_commit(&ctl.accfull[buf]);
@@ -296,25 +267,25 @@ blend_bwd_cached(int D, int ch0, int nch, int W, int H, int tile_w,
   tc_fence_before();
   __syncthreads();
   if (warp == 0) CB_STAMP(3, 0, 2);
-  if (warp == 9) tmem_dealloc<L::TCOLS>(tb);
+  if (warp == 5) tmem_dealloc<L::TCOLS>(tb);
 }
 
-template <int MB>
 int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const unsigned char *wcache,
               const int *wmeta, const int *wlist, const int *wcount, const float *v_render,
               float *v_colors, cudaStream_t st) {
-  using L = CbLayout<MB>;
+  using L = CbLayout;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
+  const int nblk = (nch + 127) / 128;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<MB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  blend_bwd_cached<MB><<<dim3(tw, hh), CB_THREADS, L::BYTES, st>>>(
-      D, ch0, nch, W, H, tw, offsets, wcache, wmeta, wlist, wcount, v_render, v_colors);
+  blend_bwd_cached<<<dim3(tw * nblk, hh), CB_THREADS, L::BYTES, st>>>(
+      D, ch0, nch, nblk, W, H, tw, offsets, wcache, wmeta, wlist, wcount, v_render, v_colors);
   return (int)cudaGetLastError();
 }
 
@@ -333,10 +304,8 @@ extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t 
   const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = (nch <= 128) ? launch_cb<1>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
-                                               wcount, v_render, v_colors, st)
-                                : launch_cb<2>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
-                                               wcount, v_render, v_colors, st);
+    const int rc = launch_cb(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount, v_render,
+                             v_colors, st);
     if (rc != 0) return rc;
   }
   return 0;
