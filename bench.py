@@ -10,8 +10,9 @@ geometry on the config-3 shape (N=2M Gaussians, 1080x1920, D=256): for each of `
 views per rank  render() -> fused L1 against a fixed random target -> backward to the per-Gaussian
 features;  then (N>1) NCCL all-reduce of the feature gradient;  then Adam on the feature table.
 value = views/sec over the whole job (all ranks), inputs resident in HBM.
-e2e   = the same loop with the per-view inputs (view matrix, target segment map + embedding table)
-        copied from pinned host memory each view and the loss read back to the host each step.
+e2e   = the same loop with the per-view training target (segment map + embedding table, the
+        inputs of the reference's read_sam_clip_feature) copied from pinned host memory each view
+        and the loss read back to the host each step.
 """
 from __future__ import annotations
 
@@ -135,7 +136,7 @@ def main():
     from gags_b200.gaussian_renderer import render
     from gags_b200.scene import GaussianModel
     from gags_b200.synthetic import CONFIGS, config_scene
-    from gags_b200.utils.loss_utils import l1_loss_fused
+    from gags_b200.utils.loss_utils import l1_loss_segmap_fused
 
     rank, world, local = parallel.init_from_env("nccl")
     if world != args.gpus and world > 1:
@@ -157,6 +158,9 @@ def main():
     pc.training_setup(OptimizationParams(), fused_optimizer=True)
     cams = [c.to(dev) for c in scene.cameras]
     n_views = len(cams)
+    # the cameras are loaded once and never written again (scene/cameras.py:58): tell the renderer,
+    # so its side-stream geometry stage need not wait for the main stream the first time it meets one
+    R.register_static(*[c.world_view_transform for c in cams])
     bg = torch.zeros(3, device=dev)
 
     # Targets: a compact (segment map, embedding table) pair per target, like the reference's
@@ -167,16 +171,14 @@ def main():
                 .repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].contiguous().pin_memory()
                 for _ in range(n_targets)]
     emb_host = [(0.1 * torch.randn(n_seg, D, generator=g)).pin_memory() for _ in range(n_targets)]
-    vm_host = [c.world_view_transform.cpu().pin_memory() for c in cams]
 
-    def assemble_target(seg_dev, emb_dev):
-        return emb_dev[seg_dev.long()]                       # [H,W,D] gather on the device
-
-    targets_dev = [assemble_target(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
+    # the targets stay in that compact form on the device as well: the fused loss gathers
+    # emb[seg] on the fly (the reference materialises the dense map every iteration, train.py:162)
+    targets_dev = [(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
 
     def one_view(cam, target):
         pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
-        loss = l1_loss_fused(pkg["render"], target)
+        loss = l1_loss_segmap_fused(pkg["render"], target[0], target[1])
         loss.backward()
         return loss
 
@@ -197,12 +199,11 @@ def main():
         loss = None
         h2d = 0
         for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
-            cam = cams[v]
-            cam.world_view_transform = vm_host[v].to(dev, non_blocking=True)
+            cam = cams[v]                 # cameras live on the device (scene/cameras.py:58)
             seg = seg_host[v % n_targets].to(dev, non_blocking=True)
             emb = emb_host[v % n_targets].to(dev, non_blocking=True)
-            h2d += vm_host[v].numel() * 4 + seg.numel() * 4 + emb.numel() * 4
-            loss = one_view(cam, assemble_target(seg, emb))
+            h2d += seg.numel() * 4 + emb.numel() * 4
+            loss = one_view(cam, (seg, emb))
         opt_step()
         return float(loss.item()), h2d                       # D2H read of the step's loss
 
@@ -230,7 +231,14 @@ def main():
         ms = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
         return ms, last, sampler.summary(), _C.launches() - l0
 
+    # Untimed priming (like the reference's scene loading): the grow-only workspaces (intersection
+    # buffers, weight-tile cache) reach their steady size, so that no cudaMalloc — a device-wide
+    # sync — lands in the timed region.  The W warm-up and K timed steps follow as the contract says.
+    priming = 6
+    for i in range(priming):
+        step_resident(10_000 + i)
     ms, _, clocks, launches = timed(step_resident, args.steps, args.warmup)
+    alloc_stats = {"reserved_GB": round(torch.cuda.max_memory_reserved(dev) / 1e9, 2)}
     views_total = args.steps * kviews * world
     value = views_total / (ms * 1e-3)
 
@@ -258,7 +266,7 @@ def main():
             cam = cams[(7 * i) % n_views]
             pkg = render(cam, pc, None, bg)
             R._mark("loss_start")
-            loss = l1_loss_fused(pkg["render"], targets_dev[0])
+            loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
             R._mark("loss")
             loss.backward()
             R._mark("backward_end")
@@ -287,6 +295,7 @@ def main():
                     "avg_launch_ms": stage_ms[kname]}
         step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4) + H * W * (4 * D + 8) + n * (4 * D + 24)
         stats["step_hbm_frac_of_8TBps"] = step_bytes / (ms * 1e-3 / (args.steps * kviews)) / 8e12
+        stats.update(alloc_stats)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -304,7 +313,9 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": f"config{args.config}: N={n}, {H}x{W}, D={D}, render + fused "
-                                       "L1 + feature backward + fused Adam (frozen geometry)",
+                                       "L1 vs emb[seg] target + feature backward + fused Adam "
+                                       "(frozen geometry)",
+                           "priming_steps": priming,
                            "views_per_step_per_gpu": kviews, "parallelism": f"view-dp{world}",
                            "l2": "inputs (2 GB feature table, 2 GB raster) exceed the 126 MB L2",
                            "optimizer_in_timed_region": True},

@@ -19,18 +19,81 @@ l1_loss_kernel(const float4 *__restrict__ r, const float4 *__restrict__ t,
                float *__restrict__ loss, float4 *__restrict__ vout) {
   float acc = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 a = ldg_nc4(r + i), b = ldg_nc4(t + i);
-    const float m = mask ? fabsf(__ldg(mask + i / d4)) : 1.f;
-    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
-    acc += m * (fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw));
-    const float s = scale * m;
-    float4 g;
-    g.x = dx > 0.f ? s : (dx < 0.f ? -s : 0.f);
-    g.y = dy > 0.f ? s : (dy < 0.f ? -s : 0.f);
-    g.z = dz > 0.f ? s : (dz < 0.f ? -s : 0.f);
-    g.w = dw > 0.f ? s : (dw < 0.f ? -s : 0.f);
-    vout[i] = g;
+  // four independent 16-B loads in flight per thread (two elements of the grid-stride sequence)
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < n4;
+    const float4 a0 = ldg_nc4(r + i0), b0 = ldg_nc4(t + i0);
+    float4 a1 = a0, b1 = b0;
+    if (two) { a1 = ldg_nc4(r + i1); b1 = ldg_nc4(t + i1); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long i = u ? i1 : i0;
+      const float4 a = u ? a1 : a0, b = u ? b1 : b0;
+      const float m = mask ? fabsf(__ldg(mask + i / d4)) : 1.f;
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+      acc += m * (fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw));
+      const float s = scale * m;
+      float4 g;
+      g.x = dx > 0.f ? s : (dx < 0.f ? -s : 0.f);
+      g.y = dy > 0.f ? s : (dy < 0.f ? -s : 0.f);
+      g.z = dz > 0.f ? s : (dz < 0.f ? -s : 0.f);
+      g.w = dw > 0.f ? s : (dw < 0.f ? -s : 0.f);
+      vout[i] = g;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_part[w];
+    atomicAdd(loss, v);
+  }
+}
+
+// Same loss with the target given in the reference's compact form: a per-pixel segment id and a
+// per-segment embedding table (what read_sam_clip_feature gathers into a dense [H,W,D] map every
+// iteration, /root/reference/scene/dataset_readers.py:54-121 called at train.py:162).  The table
+// (n_seg x D fp32, a few hundred KB) stays in L1/L2, so the pass reads 4 B per pixel instead of 4D.
+// seg < 0 = pixel without a target (weight 0).
+__global__ void __launch_bounds__(256)
+l1_loss_segmap_kernel(const float4 *__restrict__ r, const int *__restrict__ seg,
+                      const float4 *__restrict__ emb, const float *__restrict__ mask, long long n4,
+                      int d4, int n_seg, float scale, float *__restrict__ loss,
+                      float4 *__restrict__ vout) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < n4;
+    const float4 a0 = ldg_nc4(r + i0);
+    float4 a1 = a0;
+    if (two) a1 = ldg_nc4(r + i1);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long i = u ? i1 : i0;
+      const float4 a = u ? a1 : a0;
+      const long long pix = i / d4;
+      const int c4 = (int)(i - pix * d4);
+      const int sg = __ldg(seg + pix);
+      const bool ok = sg >= 0 && sg < n_seg;
+      const float4 b = ok ? __ldg(emb + (size_t)sg * d4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float m = ok ? (mask ? fabsf(__ldg(mask + pix)) : 1.f) : 0.f;
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+      acc += m * (fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw));
+      const float s = scale * m;
+      float4 g;
+      g.x = dx > 0.f ? s : (dx < 0.f ? -s : 0.f);
+      g.y = dy > 0.f ? s : (dy < 0.f ? -s : 0.f);
+      g.z = dz > 0.f ? s : (dz < 0.f ? -s : 0.f);
+      g.w = dw > 0.f ? s : (dw < 0.f ? -s : 0.f);
+      vout[i] = g;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -49,17 +112,29 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
             float4 *__restrict__ v, long long n4, float step_size, float b1, float b2,
             float omb1, float omb2, float inv_sqrt_bc2, float eps, int zero_grad) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 gi = g[i];
-    float4 mi = m[i], vi = v[i], pi = p[i];
-#define GAGS_ADAM1(c)                                             \
-    mi.c = b1 * mi.c + omb1 * gi.c;                               \
-    vi.c = b2 * vi.c + omb2 * (gi.c * gi.c);                      \
-    pi.c -= step_size * (mi.c / (sqrtf(vi.c) * inv_sqrt_bc2 + eps));
-    GAGS_ADAM1(x) GAGS_ADAM1(y) GAGS_ADAM1(z) GAGS_ADAM1(w)
+  // two independent 16-B streams per array in flight per thread (128 B per thread)
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < n4;
+    const float4 ga = g[i0];
+    float4 ma = m[i0], va = v[i0], pa = p[i0];
+    float4 gb = ga, mb = ma, vb = va, pb = pa;
+    if (two) { gb = g[i1]; mb = m[i1]; vb = v[i1]; pb = p[i1]; }
+#define GAGS_ADAM1(P, G, M, V, c)                                 \
+    M.c = b1 * M.c + omb1 * G.c;                                  \
+    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
+    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
+    GAGS_ADAM1(pa, ga, ma, va, x) GAGS_ADAM1(pa, ga, ma, va, y)
+    GAGS_ADAM1(pa, ga, ma, va, z) GAGS_ADAM1(pa, ga, ma, va, w)
+    m[i0] = ma; v[i0] = va; p[i0] = pa;
+    if (zero_grad) g[i0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (two) {
+      GAGS_ADAM1(pb, gb, mb, vb, x) GAGS_ADAM1(pb, gb, mb, vb, y)
+      GAGS_ADAM1(pb, gb, mb, vb, z) GAGS_ADAM1(pb, gb, mb, vb, w)
+      m[i1] = mb; v[i1] = vb; p[i1] = pb;
+      if (zero_grad) g[i1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #undef GAGS_ADAM1
-    m[i] = mi; v[i] = vi; p[i] = pi;
-    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -98,7 +173,7 @@ extern "C" int gags_scale_inplace(float *v, const float *scale_dev, int64_t nume
   if (numel == 0) return 0;
   const long long n4 = numel / 4;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks > 148LL * 4) blocks = 148LL * 4;
   scale_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float4 *>(v), scale_dev, n4);
   GAGS_CHECK_LAUNCH();
@@ -114,10 +189,30 @@ extern "C" int gags_l1_loss_fused(const float *render, const float *target, cons
   if (HW == 0) return 0;
   const long long n4 = (long long)HW * (D / 4);
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;   // 16 resident 256-thread CTAs per SM, grid-stride
+  if (blocks > 148LL * 8) blocks = 148LL * 8;     // half of each SM's thread slots stay free for
+                                                  // the next view's geometry stage (side stream)
   l1_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(render), reinterpret_cast<const float4 *>(target), mask, n4,
       D / 4, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int gags_l1_loss_segmap(const float *render, const int32_t *seg, const float *emb,
+                                   const float *mask, int64_t HW, int32_t D, int32_t n_seg,
+                                   float grad_scale, float *loss_out, float *v_render,
+                                   void *stream) {
+  if (!render || !seg || !emb || !loss_out || !v_render || HW < 0 || D < 1 || n_seg < 1)
+    return GAGS_EINVAL;
+  if (D % 4 != 0) return GAGS_EINVAL;
+  if (!gags_aligned16(render) || !gags_aligned16(emb) || !gags_aligned16(v_render)) return GAGS_EALIGN;
+  if (HW == 0) return 0;
+  const long long n4 = (long long)HW * (D / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  l1_loss_segmap_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(render), seg, reinterpret_cast<const float4 *>(emb), mask, n4,
+      D / 4, n_seg, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
   GAGS_CHECK_LAUNCH();
   return 0;
 }
@@ -140,7 +235,7 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   cudaStream_t st = (cudaStream_t)stream;
   if (n4 > 0) {
     long long blocks = (n4 + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks > 148LL * 4) blocks = 148LL * 4;
     adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),
         reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), n4, step_size,

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -65,6 +66,60 @@ def _mark(name: str) -> None:
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         stage_events.append((name, ev))
+
+
+# ------------------------------------------------------------------------------------------------
+# one-view lookahead: geometry stage on a side stream
+# ------------------------------------------------------------------------------------------------
+# With frozen geometry (the shipped training loop, scene/gaussian_model.py:201-206) projection,
+# tile keying and the sort of a view depend on nothing the optimiser writes, so they run on a
+# high-priority side stream and overlap the previous view's loss / backward / Adam, which are
+# HBM- or L2-bound and leave the SMs mostly idle.  All work is still done every view; only its
+# position in time changes.  Rules that keep it safe:
+#   * only when none of means / quats / scales / opacities requires grad;
+#   * the side stream waits for the whole main stream the first time it sees an input tensor
+#     (pointer + version; a strong reference is kept so the address cannot be recycled), and
+#     otherwise only for the end of the previous view's forward blend — which also bounds the
+#     lookahead (and the host run-ahead, through the n_isects readback) to one view;
+#   * every buffer produced on the side stream is record_stream()ed on the consuming stream.
+import os as _os
+lookahead = _os.environ.get("GAGS_B200_LOOKAHEAD", "1") != "0"
+_side: Dict = {}
+
+
+def _side_state(dev):
+    st = _side.get(dev.index)
+    if st is None:
+        st = dict(stream=torch.cuda.Stream(device=dev, priority=-1), ev_prev=None,
+                  seen=OrderedDict())
+        _side[dev.index] = st
+    return st
+
+
+def register_static(*tensors) -> None:
+    """Declare device tensors (camera matrices, frozen geometry) whose contents are final: after one
+    device synchronisation the side stream may read them without waiting for the main stream.
+    Optional — an unregistered tensor is simply waited for the first time it is seen."""
+    devs = {t.device for t in tensors if t.is_cuda}
+    for d in devs:
+        torch.cuda.synchronize(d)
+    for t in tensors:
+        if t.is_cuda:
+            _all_seen(_side_state(t.device), (t,))
+
+
+def _all_seen(st, tensors) -> bool:
+    seen, ok = st["seen"], True
+    for t in tensors:
+        key = (t.data_ptr(), t._version, t.numel())
+        if key in seen:
+            seen.move_to_end(key)
+        else:
+            ok = False
+            seen[key] = t
+    while len(seen) > 1024:
+        seen.popitem(last=False)
+    return ok
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,6 +262,9 @@ def tile_bits(n_tiles: int) -> int:
     return int(math.floor(math.log2(n_tiles))) + 1
 
 
+_isect_capacity = 0
+
+
 @torch.no_grad()
 def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int) -> Dict:
     """tiles_touched -> scan -> emit -> stable radix sort -> offsets.  One host sync (n_isects)."""
@@ -222,16 +280,23 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
     _C.count_launch(2)
     n = int(n_dev.item())                     # the one host sync of the pipeline
     n_tiles = tile_w * tile_h
-    keys_a = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
-    keys_b = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
-    vals_a = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    vals_b = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    # n varies by a few percent from view to view; allocating a grow-only capacity instead keeps
+    # every view's request the same size, so the caching allocator recycles blocks instead of
+    # calling cudaMalloc (a device-wide sync) every other view
+    global _isect_capacity
+    if n > _isect_capacity:
+        _isect_capacity = int(n * 1.2) + 1024
+    cap = _isect_capacity
+    keys_a = torch.empty(cap, dtype=torch.int64, device=dev)
+    keys_b = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals_a = torch.empty(cap, dtype=torch.int32, device=dev)
+    vals_b = torch.empty(cap, dtype=torch.int32, device=dev)
     offsets = torch.empty(n_tiles + 1, dtype=torch.int32, device=dev)
     if n > 0:
         _C.check(_C.lib.gags_tile_emit(_C.ptr(means2d), _C.ptr(radii), _C.ptr(depths), _C.ptr(cum),
                                        N, tile_w, tile_h, _C.ptr(keys_a), _C.ptr(vals_a), st),
                  "gags_tile_emit")
-        sws_bytes = _C.lib.gags_sort_pairs_workspace_bytes(n)
+        sws_bytes = _C.lib.gags_sort_pairs_workspace_bytes(cap)
         sws = torch.empty(sws_bytes, dtype=torch.uint8, device=dev)
         sel = ctypes.c_int32(0)
         _C.check(_C.lib.gags_sort_pairs(_C.ptr(keys_a), _C.ptr(keys_b), _C.ptr(vals_a),
@@ -244,7 +309,7 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
              "gags_tile_offsets")
     _C.count_launch()
     return dict(n_isects=n, isect_ids=keys_a[:n], flatten_ids=vals_a[:n], offsets=offsets,
-                cum_tiles=cum)
+                cum_tiles=cum, _bases=(keys_a, vals_a, offsets, cum))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -357,14 +422,39 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     tile_h = (height + TILE - 1) // TILE
     if 32 + tile_bits(tile_w * tile_h) > 64:
         raise ValueError("image too large for the 64-bit intersection key")
-    cam, keep = make_camera(viewmat, fx, fy, cx, cy, width, height, eps2d, near_plane, far_plane,
-                            radius_clip, scaling_modifier, flags)
-    _mark("start")
-    radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
-        means, quats, scales, opacities, cam, keep, tile_w, tile_h)
-    _mark("project")
-    binned = bin_and_sort(means2d.detach(), radii, depths.detach(), tiles, tile_w, tile_h)
-    _mark("bin_sort")
+    geo_in = (means, quats, scales, opacities)
+    use_side = (lookahead and stage_events is None and means.is_cuda and viewmat.is_cuda
+                and not any(t.requires_grad for t in geo_in))
+    if use_side:
+        dev = means.device
+        main = torch.cuda.current_stream(dev)
+        ss = _side_state(dev)
+        side = ss["stream"]
+        if not _all_seen(ss, geo_in + (viewmat,)):
+            side.wait_stream(main)
+        elif ss["ev_prev"] is not None:
+            side.wait_event(ss["ev_prev"])
+        with torch.cuda.stream(side):
+            cam, keep = make_camera(viewmat, fx, fy, cx, cy, width, height, eps2d, near_plane,
+                                    far_plane, radius_clip, scaling_modifier, flags)
+            radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
+                means, quats, scales, opacities, cam, keep, tile_w, tile_h)
+            binned = bin_and_sort(means2d, radii, depths, tiles, tile_w, tile_h)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        main.wait_event(ev)
+        for t in (radii, means2d, depths, conics, opac, tiles, geom, keep) + binned["_bases"]:
+            if t is not None:
+                t.record_stream(main)
+    else:
+        cam, keep = make_camera(viewmat, fx, fy, cx, cy, width, height, eps2d, near_plane,
+                                far_plane, radius_clip, scaling_modifier, flags)
+        _mark("start")
+        radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
+            means, quats, scales, opacities, cam, keep, tile_w, tile_h)
+        _mark("project")
+        binned = bin_and_sort(means2d.detach(), radii, depths.detach(), tiles, tile_w, tile_h)
+        _mark("bin_sort")
     if sh_degree is None:
         cols = colors
         if cols.dim() != 2 or cols.shape[0] != means.shape[0]:
@@ -393,6 +483,9 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
                                             binned["offsets"], binned["flatten_ids"], width, height)
     _mark("blend_fwd")
+    if use_side:
+        ss["ev_prev"] = torch.cuda.Event()
+        ss["ev_prev"].record(main)
     if pad:
         render = render[..., :D]
     if render_mode in ("ED", "RGB+ED"):

@@ -194,6 +194,14 @@ int gags_l1_loss_fused(const float *render, const float *target, const float *ma
                        int32_t D, float grad_scale, float *loss_out, float *v_render,
                        void *stream);
 
+/* The same loss with the target in the reference's compact per-view form — seg[HW] int32 segment
+ * ids (< 0 = no target) and emb[n_seg, D] per-segment embeddings, i.e. the inputs that
+ * read_sam_clip_feature (/root/reference/scene/dataset_readers.py:54-121, train.py:162) gathers into
+ * a dense map every iteration: target[p, :] = emb[seg[p], :].  No dense target is materialised.  */
+int gags_l1_loss_segmap(const float *render, const int32_t *seg, const float *emb,
+                        const float *mask, int64_t HW, int32_t D, int32_t n_seg, float grad_scale,
+                        float *loss_out, float *v_render, void *stream);
+
 /* v[0..numel) *= *scale_dev (a DEVICE scalar), a no-op pass when the scalar is exactly 1: chains the
  * fused loss's stored gradient with autograd's incoming grad_output without a host sync and, in the
  * usual loss.backward() case, without touching the 2 GB buffer.  numel % 4 == 0.                */

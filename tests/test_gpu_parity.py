@@ -471,6 +471,29 @@ def test_fused_l1_chains_grad_output():
         assert rel_err(a.grad, b.grad) < 1e-6
 
 
+def test_fused_l1_segmap_equals_dense_target():
+    """l1_loss_segmap_fused(render, seg, emb) == l1_loss(render, emb[seg]) with seg < 0 pixels excluded
+    (the compact target form of read_sam_clip_feature, scene/dataset_readers.py:54-121)."""
+    from gags_b200.utils.loss_utils import l1_loss_segmap_fused
+    g = torch.Generator().manual_seed(5)
+    H, W, D, S = 37, 53, 48, 11
+    r = torch.randn(H, W, D, generator=g).cuda()
+    seg = torch.randint(-1, S, (H, W), generator=g, dtype=torch.int32).cuda()
+    emb = torch.randn(S, D, generator=g).cuda()
+    mask = torch.rand(H, W, generator=g).cuda()
+    for m in (None, mask):
+        a = r.clone().requires_grad_(True)
+        b = r.clone().requires_grad_(True)
+        loss = l1_loss_segmap_fused(a.permute(2, 0, 1), seg, emb, m)
+        loss.backward()
+        valid = (seg >= 0).float()[..., None] * (1.0 if m is None else m[..., None])
+        dense = emb[seg.clamp_min(0).long()]
+        ref = ((b - dense).abs() * valid).mean()
+        ref.backward()
+        assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+        assert rel_err(a.grad, b.grad) < 1e-6
+
+
 def test_fused_adam_matches_torch_adam():
     from gags_b200.optim import FusedAdam
     g = torch.Generator().manual_seed(8)
