@@ -189,8 +189,7 @@ extern "C" int gags_l1_loss_fused(const float *render, const float *target, cons
   if (HW == 0) return 0;
   const long long n4 = (long long)HW * (D / 4);
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 8) blocks = 148LL * 8;     // half of each SM's thread slots stay free for
-                                                  // the next view's geometry stage (side stream)
+  if (blocks > 148LL * 8) blocks = 148LL * 8;     // 8 resident 256-thread CTAs per SM, grid-stride
   l1_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(render), reinterpret_cast<const float4 *>(target), mask, n4,
       D / 4, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
@@ -235,6 +234,8 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   cudaStream_t st = (cudaStream_t)stream;
   if (n4 > 0) {
     long long blocks = (n4 + 255) / 256;
+    // half of each SM's thread slots stay free: this pass is a pure HBM stream and the next view's
+    // geometry stage runs beside it on the side stream (rasterization.lookahead)
     if (blocks > 148LL * 4) blocks = 148LL * 4;
     adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),

@@ -354,6 +354,18 @@ class _Blend(torch.autograd.Function):
                                            _C.stream_ptr()), "gags_blend_fwd")
         _C.count_launch((D + 255) // 256 if D > 32 else 1)
         ctx.dims = (width, height, D, N)
+        # The backward accumulates into a zeroed [N, D] buffer (2 GB at config 3).  Zeroing it is a
+        # pure HBM stream, the forward above is instruction-bound with its shared memory full: the
+        # fill runs beside it on the side stream instead of in front of the backward.
+        ctx.prezero = None
+        if cache is not None and lookahead and stage_events is None:
+            main = torch.cuda.current_stream(dev)
+            side = _side_state(dev)["stream"]
+            with torch.cuda.stream(side):
+                vz = torch.zeros(N, D, dtype=torch.float32, device=dev)
+                evz = torch.cuda.Event()
+                evz.record(side)
+            ctx.prezero = (vz, evz, main)
         ctx.lease = lease if cache is not None else None
         ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
         ctx.mark_non_differentiable(last_ids)
@@ -372,7 +384,14 @@ class _Blend(torch.autograd.Function):
         v_render = _f32c(v_render)
         st = _C.stream_ptr()
         _mark("bwd_start")
-        v_colors = torch.zeros(N, D, device=dev) if need_col else None
+        if need_col and ctx.prezero is not None:
+            v_colors, evz, _ = ctx.prezero
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(evz)
+            v_colors.record_stream(cur)
+            ctx.prezero = None
+        else:
+            v_colors = torch.zeros(N, D, device=dev) if need_col else None
         _mark("bwd_zero")
         v_m = v_c = v_o = v_bg = None
         if not need_geo:
