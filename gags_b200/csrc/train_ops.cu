@@ -234,8 +234,7 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   cudaStream_t st = (cudaStream_t)stream;
   if (n4 > 0) {
     long long blocks = (n4 + 255) / 256;
-    // half of each SM's thread slots stay free: this pass is a pure HBM stream and the next view's
-    // geometry stage runs beside it on the side stream (rasterization.lookahead)
+    // half of each SM's thread slots stay free next to this pure HBM stream
     if (blocks > 148LL * 4) blocks = 148LL * 4;
     adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),

@@ -73,9 +73,11 @@ def _mark(name: str) -> None:
 # ------------------------------------------------------------------------------------------------
 # With frozen geometry (the shipped training loop, scene/gaussian_model.py:201-206) projection,
 # tile keying and the sort of a view depend on nothing the optimiser writes, so they run on a
-# high-priority side stream and overlap the previous view's loss / backward / Adam, which are
-# HBM- or L2-bound and leave the SMs mostly idle.  All work is still done every view; only its
-# position in time changes.  Rules that keep it safe:
+# high-priority side stream and overlap the previous view's loss / backward.  All work is still
+# done every view; only its position in time changes.  Measured on B200 (tools/trace_step.py): the
+# gain is modest (~0.3 ms of the 1.0 ms stage) because the sort and the L2-reduction-bound backward
+# slow each other down; starting the stage beside Adam instead needs a shared-memory carveout on
+# the Adam kernel and then costs Adam as much as it saves.  Rules that keep it safe:
 #   * only when none of means / quats / scales / opacities requires grad;
 #   * the side stream waits for the whole main stream the first time it sees an input tensor
 #     (pointer + version; a strong reference is kept so the address cannot be recycled), and
