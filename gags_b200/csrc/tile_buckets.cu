@@ -1,0 +1,206 @@
+// tile_buckets.cu — K4-K6 as a tile-bucketed segmented sort (the "warp/block-level radix sort with
+// a global bucketing pass" of north_star), bit-identical in its outputs to the global path of
+// tiles.cu (gsplat isect_tiles + cub::DeviceRadixSort::SortPairs + isect_offset_encode, reached
+// from /root/reference/gaussian_renderer/__init__.py:56-70).
+//
+// The reference order is a stable sort of (tile << 32 | depth_bits) over intersections emitted in
+// ascending Gaussian index, i.e. inside a tile: ascending depth bits, ties by ascending Gaussian
+// index.  A Gaussian meets a tile at most once, so (depth_bits, gaussian) is a unique key inside a
+// tile and the same order is obtained without any global sort:
+//   1. tile_hist     count[t] += 1 for every (Gaussian, tile) pair            (L2 atomics)
+//   2. bucket_scan   offsets[t] = exclusive sum  -> this IS isect_offsets; n_isects and the largest
+//                    bucket come out as two extra ints (one host readback, as before)
+//   3. tile_scatter  slot = offsets[t] + cursor[t]++ ; bucket[slot] = depth_bits << gbits | gaussian
+//   4. bucket_sort   one CTA per tile: cub::BlockRadixSort of the tile's keys in shared memory,
+//                    write flatten_ids (and isect_ids for the caller's info dict)
+// HBM traffic: 24 B/Gaussian twice + 8 B/intersection written, read, then 12 B written — about a
+// fifth of the 6-pass global radix sort.  Buckets larger than BUCKET_MAX make the caller fall back
+// to the global path.
+#include "common.cuh"
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+
+namespace {
+
+constexpr int COOP = 32;
+constexpr int SORT_THREADS = 256;
+constexpr int BUCKET_MAX = SORT_THREADS * 16;
+
+// visits every tile of every Gaussian: small footprints per thread, large ones by the whole warp
+template <class F>
+__device__ __forceinline__ void for_each_tile(const float2 *__restrict__ means2d,
+                                              const int *__restrict__ radii, long long N, int tile_w,
+                                              int tile_h, F f) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, x1 = 0, y0 = 0, y1 = 0, cnt = 0;
+  if (i < N && radii[i] > 0) {
+    const float2 m = means2d[i];
+    tile_bounds(m.x, m.y, radii[i], tile_w, tile_h, x0, x1, y0, y1);
+    cnt = (x1 - x0) * (y1 - y0);
+  }
+  if (cnt > 0 && cnt < COOP) {
+    for (int ty = y0; ty < y1; ++ty)
+      for (int tx = x0; tx < x1; ++tx) f(ty * tile_w + tx, i);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt >= COOP);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src);
+    const int by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
+    const long long gid = i - lane + src;
+    const int nx = bx1 - bx0;
+    for (int k = lane; k < bcnt; k += 32) f((by0 + k / nx) * tile_w + bx0 + k % nx, gid);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tile_hist_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii, long long N,
+                 int tile_w, int tile_h, int *__restrict__ count) {
+  for_each_tile(means2d, radii, N, tile_w, tile_h,
+                [&](int t, long long) { atomicAdd(count + t, 1); });
+}
+
+// single CTA: exclusive scan of count[n_tiles] -> offsets[n_tiles + 1]; stats = {n_isects, max}
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(const int *__restrict__ count, int n_tiles, int *__restrict__ offsets,
+                   int *__restrict__ stats) {
+  using Scan = cub::BlockScan<int, 1024>;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ int s_max[32];
+  int base = 0, mx = 0;
+  for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const int t = t0 + threadIdx.x;
+    const int c = t < n_tiles ? count[t] : 0;
+    mx = max(mx, c);
+    int ex, total;
+    Scan(tmp).ExclusiveSum(c, ex, total);
+    if (t < n_tiles) offsets[t] = base + ex;
+    base += total;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
+    offsets[n_tiles] = base;
+    stats[0] = base;
+    stats[1] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii,
+                    const float *__restrict__ depths, long long N, int tile_w, int tile_h,
+                    int gbits, const int *__restrict__ offsets, int *__restrict__ cursor,
+                    unsigned long long *__restrict__ bucket) {
+  for_each_tile(means2d, radii, N, tile_w, tile_h, [&](int t, long long gid) {
+    const unsigned long long key =
+        ((unsigned long long)__float_as_uint(__ldg(depths + gid)) << gbits) | (unsigned long long)gid;
+    const int slot = __ldg(offsets + t) + atomicAdd(cursor + t, 1);
+    bucket[slot] = key;
+  });
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void sort_bucket(const unsigned long long *__restrict__ src, int cnt,
+                                            int tile, int gbits, long long *__restrict__ keys_out,
+                                            int *__restrict__ ids_out, void *smem) {
+  using Sort = cub::BlockRadixSort<unsigned long long, SORT_THREADS, ITEMS, cub::NullType, 6>;
+  typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
+  unsigned long long k[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int idx = j * SORT_THREADS + threadIdx.x;          // striped load (coalesced)
+    k[j] = idx < cnt ? src[idx] : ~0ull;
+  }
+  // the initial arrangement is irrelevant (keys are unique); result: striped, ascending
+  Sort(tmp).SortBlockedToStriped(k, 0, 32 + gbits);
+  const unsigned long long gmask = (1ull << gbits) - 1ull;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int idx = j * SORT_THREADS + threadIdx.x;
+    if (idx < cnt) {
+      ids_out[idx] = (int)(k[j] & gmask);
+      if (keys_out) keys_out[idx] = ((long long)tile << 32) | (long long)(k[j] >> gbits);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+bucket_sort_kernel(const unsigned long long *__restrict__ bucket, const int *__restrict__ offsets,
+                   int gbits, long long *__restrict__ isect_ids, int *__restrict__ flatten_ids) {
+  __shared__ __align__(16) unsigned char smem[sizeof(
+      typename cub::BlockRadixSort<unsigned long long, SORT_THREADS, 16, cub::NullType, 6>::TempStorage)];
+  const int tile = blockIdx.x;
+  const int s = offsets[tile], cnt = offsets[tile + 1] - s;
+  if (cnt <= 0) return;
+  const unsigned long long *src = bucket + s;
+  long long *ko = isect_ids ? isect_ids + s : nullptr;
+  int *io = flatten_ids + s;
+  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, gbits, ko, io, smem);
+  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, gbits, ko, io, smem);
+  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, gbits, ko, io, smem);
+  else sort_bucket<16>(src, cnt, tile, gbits, ko, io, smem);
+}
+
+}  // namespace
+
+extern "C" int32_t gags_tile_bucket_max(void) { return BUCKET_MAX; }
+
+// Steps 1-2.  count[n_tiles] is scratch (zeroed here); offsets[n_tiles + 1]; stats_dev[2] =
+// {n_isects, largest bucket}.
+extern "C" int gags_tile_bucket_count(const float *means2d, const int32_t *radii, int64_t N,
+                                      int32_t tile_w, int32_t tile_h, int32_t *count,
+                                      int32_t *offsets, int32_t *stats_dev, void *stream) {
+  if (!means2d || !radii || !count || !offsets || !stats_dev || N < 0 || tile_w <= 0 || tile_h <= 0)
+    return GAGS_EINVAL;
+  if ((long long)tile_w * tile_h > 0x3fffffffLL) return GAGS_ERANGE;
+  if (((uintptr_t)means2d) & 7u) return GAGS_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_tiles = tile_w * tile_h;
+  GAGS_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)n_tiles, st));
+  if (N > 0) {
+    tile_hist_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float2 *>(means2d), radii, (long long)N, tile_w, tile_h, count);
+    GAGS_CHECK_LAUNCH();
+  }
+  bucket_scan_kernel<<<1, 1024, 0, st>>>(count, n_tiles, offsets, stats_dev);
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+// Steps 3-4.  cursor[n_tiles] scratch (zeroed here), bucket[n_isects] scratch (8 B each);
+// isect_ids may be NULL.  Requires the largest bucket <= gags_tile_bucket_max() (GAGS_ERANGE is
+// the caller's cue to use the global sort instead) and N <= 2^31.
+extern "C" int gags_tile_bucket_sort(const float *means2d, const int32_t *radii, const float *depths,
+                                     int64_t N, int32_t tile_w, int32_t tile_h,
+                                     const int32_t *offsets, int32_t max_bucket, int32_t *cursor,
+                                     void *bucket, int64_t *isect_ids, int32_t *flatten_ids,
+                                     void *stream) {
+  if (!means2d || !radii || !depths || !offsets || !cursor || !bucket || !flatten_ids || N < 0 ||
+      tile_w <= 0 || tile_h <= 0)
+    return GAGS_EINVAL;
+  if (max_bucket > BUCKET_MAX || N > 0x7fffffffLL) return GAGS_ERANGE;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_tiles = tile_w * tile_h;
+  int gbits = 1;
+  while ((1LL << gbits) < N) ++gbits;
+  GAGS_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)n_tiles, st));
+  tile_scatter_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const float2 *>(means2d), radii, depths, (long long)N, tile_w, tile_h, gbits,
+      offsets, cursor, reinterpret_cast<unsigned long long *>(bucket));
+  GAGS_CHECK_LAUNCH();
+  bucket_sort_kernel<<<n_tiles, SORT_THREADS, 0, st>>>(
+      reinterpret_cast<const unsigned long long *>(bucket), offsets, gbits,
+      reinterpret_cast<long long *>(isect_ids), flatten_ids);
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}

@@ -77,12 +77,23 @@ def test_fused_activations_match_reference_getters():
     assert rel_err(b["opac"].cpu(), sc["opacities"]) < 1e-6
 
 
-@pytest.mark.parametrize("seed,n,w,h", [(0, 3000, 160, 96), (3, 20000, 320, 200), (5, 64, 1920, 1080)])
-def test_tile_stage_is_bit_exact(seed, n, w, h):
+@pytest.mark.parametrize("bucketed", [True, False])
+@pytest.mark.parametrize("seed,n,w,h", [(0, 3000, 160, 96), (3, 20000, 320, 200), (5, 64, 1920, 1080),
+                                        (7, 9000, 48, 32)])
+def test_tile_stage_is_bit_exact(seed, n, w, h, bucketed):
+    """both K4-K6 implementations (tile-bucketed segmented sort / global radix sort) against the
+    oracle; the last case has > 4096 intersections per tile, which makes the bucketed path fall
+    back to the global sort by itself."""
+    from gags_b200 import rasterization as R
     sc = front_scene(n, w, h, 3, seed=seed, sigma_px=(0.5, 30.0))
     if n == 64:
         sc["scales"] *= 40.0                                   # screen-filling Gaussians (coop emit)
-    st = _stages(sc)
+    default = R.bucket_sort
+    R.bucket_sort = bucketed
+    try:
+        st = _stages(sc)
+    finally:
+        R.bucket_sort = default
     m2d, radii, dep = st["means2d"].cpu(), st["radii"].cpu(), st["depths"].cpu()
     cnt, keys, vals = O.isect_tiles(m2d, radii, dep, st["tw"], st["th"])
     assert torch.equal(st["tiles"].cpu(), cnt)
