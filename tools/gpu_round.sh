@@ -1,6 +1,6 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, a short bench, ncu launch list + full capture of the
-# blend kernels.  Logs land in gpurun_out/.
+# One GPU-box visit: parity tests, smoke, a bench, ncu launch list + full capture of the blend
+# kernels.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt
@@ -8,14 +8,15 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pyt
 echo "pytest rc=${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+timeout 900 python bench.py --steps ${STEPS:-20} --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline \
     > gpurun_out/ncu_launch.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 2 -c 2 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 8 -c 2 \
     -f -o gpurun_out/prof_blend python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline \
     > gpurun_out/ncu_full.log 2>&1
 fi
-tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err; cat gpurun_out/bench_ref.log

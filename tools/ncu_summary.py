@@ -73,6 +73,23 @@ def full(src, dst):
                     i = hdr.index(m)
                     f.write(f"| {m} | {r[i]} | {units[i]} |\n")
             f.write("\n")
+    # DRAM bytes per launch of the two blend kernels -> profiles/traffic.json (read by bench.py)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic = {}
+    for r in rows[2:]:
+        name = short(r[hdr.index("Kernel Name")])
+        key = "blend_fwd" if "blend_fwd" in name else ("blend_bwd" if "blend_bwd" in name else None)
+        if key is None:
+            continue
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        traffic[key] = int(tot)
+    if traffic:
+        import json, os
+        with open(os.path.join(os.path.dirname(dst), "traffic.json"), "w") as f:
+            json.dump(traffic, f)
 
 
 if __name__ == "__main__":
