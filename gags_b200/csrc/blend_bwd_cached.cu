@@ -48,7 +48,7 @@ constexpr int CB_THREADS = 192;   // warps 0-3 staging + epilogue, 4 bulk-copy p
 struct CbCtl {
   uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull;
   uint32_t tmem_base;
-  uint32_t nzmask[4];         // per epilogue warp: Gaussians with a non-zero row
+  uint32_t nzmask[2][4];      // per staging buffer and epilogue warp: Gaussians with a non-zero row
 };
 
 // One CTA = one 16x8 half tile x one block of 128 channels; two CTAs per SM, so one CTA's v_render
@@ -57,9 +57,9 @@ struct CbLayout {
   static constexpr int VPART = 32768;                  // one bf16 part (hi or lo): 128 px x 128 ch
   static constexpr int V_OFF = 0;
   static constexpr int W_OFF = 2 * VPART;              // 2 stages x one 16 KB weight tile
-  static constexpr int STG_OFF = W_OFF + 32768;        // [16 g][128 ch] fp32
-  static constexpr int CTL_OFF = STG_OFF + 8192;
-  static constexpr int BYTES = CTL_OFF + (int)sizeof(CbCtl) + 1024;
+  static constexpr int STG_OFF = W_OFF + 32768;        // 2 x [16 g][128 ch] fp32
+  static constexpr int CTL_OFF = STG_OFF + 16384;
+  static constexpr int BYTES = CTL_OFF + (int)sizeof(CbCtl);   // no slack: base must be 1 KB aligned
   static constexpr int TCOLS = 128;                    // 2 accumulator buffers x [hi(32) | lo(32)]
 };
 static_assert(CbLayout::BYTES <= (233472 / 2 - 1024), "cached backward must fit twice per SM");
@@ -72,6 +72,9 @@ __device__ __forceinline__ void bulk_red_add_f32(float *gdst, const void *ssrc, 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(CB_THREADS, 2)
@@ -93,8 +96,12 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
   const int cfirst = ch0 + cblk * 128;               // first channel of this CTA
   const int cvalid = min(128, nch - cblk * 128);     // channels of this block that exist (% 16 == 0)
 
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // The kernel has no static shared memory, so the dynamic window starts at the CTA's shared-memory
+  // base (1 KB aligned, which SWIZZLE_128B needs); the layout uses every byte of the two-CTAs-per-SM
+  // budget, so this is checked instead of padded.
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  unsigned char *sm = smem_raw;
   unsigned char *sV = sm + L::V_OFF;
   unsigned char *sW = sm + L::W_OFF;
   CbCtl &ctl = *reinterpret_cast<CbCtl *>(sm + L::CTL_OFF);
@@ -170,7 +177,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
     // Epilogue: the four warps are the four TMEM lane quarters = 128 channels.  Per step: TMEM ->
     // registers -> [16 g][128 ch] fp32 in shared memory (two passes) -> one bulk async reduction
     // (TMA add at L2) per Gaussian row, 512 B contiguous.
-    float *stg = reinterpret_cast<float *>(sm + L::STG_OFF);
+    float *stg0 = reinterpret_cast<float *>(sm + L::STG_OFF);
     for (int gi = 0; gi < nbat; ++gi) {
       const int buf = gi & 1;
       // Gaussian row this lane reduces into (warp 0 issues): straight from the cached ids
@@ -201,25 +208,30 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
       uint32_t nz = 0;
 #pragma unroll
       for (int g = 0; g < 32; ++g) nz |= __any_sync(0xffffffffu, acc[g] != 0.f) ? (1u << g) : 0u;
+      // two staging buffers, one per half: the bulk reductions of one half drain (TMA reads shared
+      // memory at the L2 reduction rate) while the other half and the next step are produced
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        named_bar_sync(2, 128);                      // staging buffer free (issuer waited the reads)
+        float *stg = stg0 + half * 2048;
+        if (warp == 0) bulk_wait_read1();            // this buffer's previous reductions have left smem
+        named_bar_sync(2, 128);
 #pragma unroll
         for (int g = 0; g < 16; ++g) stg[g * 128 + q * 32 + lane] = acc[half * 16 + g];
-        if (lane == 0) ctl.nzmask[q] = nz;
+        if (lane == 0) ctl.nzmask[half][q] = nz;
         fence_async_smem();
         named_bar_sync(2, 128);
         if (warp == 0) {
-          const uint32_t any = ctl.nzmask[0] | ctl.nzmask[1] | ctl.nzmask[2] | ctl.nzmask[3];
+          const uint32_t any = ctl.nzmask[half][0] | ctl.nzmask[half][1] | ctl.nzmask[half][2] |
+                               ctl.nzmask[half][3];
           const int g = lane - half * 16;            // lanes [16 half, 16 half + 16) issue
           if (g >= 0 && g < 16 && gid >= 0 && cvalid > 0 && ((any >> lane) & 1u))
             bulk_red_add_f32(v_colors + (size_t)gid * D + cfirst, stg + g * 128, (uint32_t)cvalid * 4u);
           bulk_commit();
-          bulk_wait_read0();
         }
       }
       if (warp == 0) CB_STAMP(0, gi, 3);
     }
+    if (warp == 0) bulk_wait_read0();                // shared memory must outlive the last reads
   } else if (warp == 4) {
     // ======================= bulk-copy producer: one cached weight tile per step ====================
     if (lane == 0) {
