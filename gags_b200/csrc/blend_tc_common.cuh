@@ -26,8 +26,36 @@ __device__ __forceinline__ bool tc_alpha_extent(float a, float b, float c, float
   return true;
 }
 
+// Exact (conservative only by the fp32 slack) test "does the ellipse {sigma <= Lm} reach the
+// rectangle of pixel centres [x_lo, x_hi] x [y_lo, y_hi]": sigma is a convex quadratic, so its minimum
+// over the rectangle is 0 when the mean is inside and otherwise sits on one of the four edges, where
+// it is a clamped 1-D minimisation.  Culls ~15 % of the bounding-box survivors at config 3
+// (tools/workload_stats.py): diagonal / elongated footprints whose box clips a corner.
+__device__ __forceinline__ bool tc_ellipse_hits_rect(float mx, float my, float a, float b, float c,
+                                                     float Lm, float x_lo, float x_hi, float y_lo,
+                                                     float y_hi) {
+  if (mx >= x_lo && mx <= x_hi && my >= y_lo && my <= y_hi) return true;
+  if (!(a > 0.f && c > 0.f)) return true;
+  float best = 3.0e38f;
+  const float ia = __fdividef(1.f, a), ic = __fdividef(1.f, c);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float dx = (k ? x_hi : x_lo) - mx;
+    const float dy = fminf(fmaxf(-b * dx * ic, y_lo - my), y_hi - my);
+    best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float dy = (k ? y_hi : y_lo) - my;
+    const float dx = fminf(fmaxf(-b * dy * ia, x_lo - mx), x_hi - mx);
+    best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
+  }
+  return best <= Lm * 1.0002f + 2e-3f;
+}
+
 // 4-bit mask of the 8x4 pixel blocks of the 16x8 half tile at (hx0, hy0) (= first pixel CENTRE)
-// that the Gaussian's alpha >= 1/255 bounding box touches.
+// that the Gaussian's alpha >= 1/255 bounding box touches; 0 when the bounding box misses the half
+// tile or the ellipse itself does.
 __device__ __forceinline__ unsigned tc_block_mask(const float4 &g0, const float4 &g1, float hx0,
                                                   float hy0) {
   float hx, hy;
@@ -38,6 +66,11 @@ __device__ __forceinline__ unsigned tc_block_mask(const float4 &g0, const float4
     for (int b = 0; b < 4; ++b) {
       const float bx = hx0 + (float)((b & 1) << 3), by = hy0 + (float)((b >> 1) << 2);
       if (ux >= bx && lx <= bx + 7.f && uy >= by && ly <= by + 3.f) mask |= 1u << b;
+    }
+    if (mask != 0u) {
+      const float Lm = fmaxf(__logf(255.f * g1.y), 0.f) + 2e-3f;
+      if (!tc_ellipse_hits_rect(g0.x, g0.y, g0.z, g0.w, g1.x, Lm, hx0, hx0 + 15.f, hy0, hy0 + 7.f))
+        mask = 0u;
     }
   }
   return mask;

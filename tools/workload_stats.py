@@ -68,3 +68,41 @@ def m(x): return sum(x) / max(len(x), 1)
 print(f"half tiles sampled {len(acc['L'])}: list {m(acc['L']):.0f}  bbox-survivors {m(acc['S']):.0f}  scanned-until-stop {m(acc['stop_scan']):.0f} "
       f"survivors-until-stop {m(acc['stop_surv']):.0f} (of which contributing {m(acc['S_proc_nz']):.0f})  batches/half-tile {m([math.ceil(x/32) for x in acc['stop_surv']]):.1f}  "
       f"K_eff/pixel {m(acc['keff']):.1f}  block occupancy {m(acc['blk']):.2f}")
+
+# ---- how much would an exact ellipse-vs-rectangle test cull beyond the bounding box? -----------------
+def min_sigma_rect(mm, cc, x_lo, x_hi, y_lo, y_hi):
+    """min over the rectangle of sigma = .5(a dx^2 + c dy^2) + b dx dy (convex quadratic)."""
+    a, b, c = cc[:, 0], cc[:, 1], cc[:, 2]
+    mx, my = mm[:, 0], mm[:, 1]
+    inside = (mx >= x_lo) & (mx <= x_hi) & (my >= y_lo) & (my <= y_hi)
+    best = torch.full_like(a, float("inf"))
+    for xe in (x_lo, x_hi):                       # vertical edges: x fixed, minimise over y
+        dx = xe - mx
+        dy = (-b * dx / c).clamp(y_lo - my, y_hi - my)
+        best = torch.minimum(best, 0.5 * (a * dx * dx + c * dy * dy) + b * dx * dy)
+    for ye in (y_lo, y_hi):
+        dy = ye - my
+        dx = (-b * dy / a).clamp(x_lo - mx, x_hi - mx)
+        best = torch.minimum(best, 0.5 * (a * dx * dx + c * dy * dy) + b * dx * dy)
+    return torch.where(inside, torch.zeros_like(best), best)
+
+tot_bbox = tot_exact = 0
+for t in sample[:60]:
+    s, e = o2[t], o2[t + 1]
+    if e <= s: continue
+    ty, tx = divmod(t, tw)
+    sel = ids[s:e].long()
+    mm, cc, oo = m2d[sel], con[sel], op[sel]
+    for half in range(2):
+        y0 = ty * 16 + half * 8
+        if y0 >= H: continue
+        Lg = torch.log(255.0 * oo)
+        det = cc[:, 0] * cc[:, 2] - cc[:, 1] ** 2
+        Lm = Lg.clamp_min(0) + 2e-3
+        hx = torch.sqrt(2 * Lm / det * cc[:, 2]) * 1.0005 + 0.02
+        hy = torch.sqrt(2 * Lm / det * cc[:, 0]) * 1.0005 + 0.02
+        x_lo, x_hi, y_lo, y_hi = tx * 16 + 0.5, tx * 16 + 15.5, y0 + 0.5, y0 + 7.5
+        keep = (Lg > -1e-3) & (mm[:, 0] + hx >= x_lo) & (mm[:, 0] - hx <= x_hi) & (mm[:, 1] + hy >= y_lo) & (mm[:, 1] - hy <= y_hi)
+        exact = keep & (min_sigma_rect(mm, cc, x_lo, x_hi, y_lo, y_hi) <= Lm)
+        tot_bbox += int(keep.sum()); tot_exact += int(exact.sum())
+print(f"exact ellipse-vs-rectangle cull keeps {tot_exact} of {tot_bbox} bbox survivors ({100*tot_exact/max(tot_bbox,1):.1f} %)")
