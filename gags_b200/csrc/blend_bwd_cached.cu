@@ -20,8 +20,8 @@
 // contiguous: the adds happen at L2 and the SM's LSU issues 32 instructions per tile instead of
 // 256 vector reds, which measured ~130 cycles each per SM) while the next step's MMAs run.
 //
-// Warps: 0-3 v_render staging then epilogue (the four TMEM lane quarters), 4 bulk-copy producer,
-// 5 MMA issue.  Two CTAs per SM.
+// Warps: 0-3 v_render staging, 4-7 epilogue (the four TMEM lane quarters), 8 bulk-copy producer,
+// 9 MMA issue.  Persistent, two CTAs per SM.
 //
 // Roofline: HBM — H*W*4D (v_render, once) + 16.1 KB per cached batch + N_contrib*4D*2 (reduction
 // target; the reductions resolve in L2).
@@ -43,16 +43,27 @@ extern "C" int gags_debug_timeline_bwd(long long *host_dst, int n) {
 
 namespace {
 
-constexpr int CB_THREADS = 192;   // warps 0-3 staging + epilogue, 4 bulk-copy producer, 5 MMA issue
+constexpr int CB_THREADS = 320;   // warps 0-3 v_render staging, 4-7 epilogue, 8 bulk-copy producer,
+                                  // 9 MMA issue
+
+constexpr int CB_JQ = 8;          // job-id ring (roles are never more than 4 jobs apart, see below)
 
 struct CbCtl {
-  uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull;
+  uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull, vfree;
+  uint64_t jq_full[CB_JQ];
   uint32_t tmem_base;
   uint32_t nzmask[2][4];      // per staging buffer and epilogue warp: Gaussians with a non-zero row
+  int jobq[CB_JQ];
 };
 
-// One CTA = one 16x8 half tile x one block of 128 channels; two CTAs per SM, so one CTA's v_render
-// staging (HBM latency) hides behind the other's MMAs and reductions.
+// One job = one 16x8 half tile x one block of 128 channels.  Persistent CTAs (two per SM) pull job
+// ids from a global counter (dynamic: a CTA that is dispatched late — e.g. behind a higher-priority
+// side-stream kernel — simply finds less work left); inside a CTA the staging warps already load
+// the NEXT job's v_render block (64 KB, pure HBM latency) while the epilogue warps are still
+// reducing the current job's last steps — the reductions, not the MMAs, are what a job spends most
+// of its time on.  Job ids travel through a ring of CB_JQ slots filled by staging warp 0: fetching
+// job k needs vfull(k-1), hence vfree(k-2), hence every MMA of job k-2 issued, hence (accumulator
+// double buffering) the epilogue at job >= k-4: no role is more than 4 jobs behind the fetcher.
 struct CbLayout {
   static constexpr int VPART = 32768;                  // one bf16 part (hi or lo): 128 px x 128 ch
   static constexpr int V_OFF = 0;
@@ -77,25 +88,36 @@ __device__ __forceinline__ void bulk_wait_read1() {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
+// what every role needs to know about a job; all roles enumerate the jobs identically
+struct CbJob {
+  int nbat, hbase, x0, y0, cfirst, cvalid;
+};
+__device__ __forceinline__ CbJob cb_job(long long j, int nblk, int tile_w, int ch0, int nch,
+                                        const int *__restrict__ offsets,
+                                        const int *__restrict__ wcount) {
+  CbJob jb;
+  const int per_row = tile_w * nblk;
+  const int by = (int)(j / per_row), bx = (int)(j - (long long)by * per_row);
+  const int tx = bx / nblk, cblk = bx - tx * nblk;
+  jb.nbat = __ldg(wcount + by * tile_w + tx);
+  const int tile = (by >> 1) * tile_w + tx;
+  const int s = __ldg(offsets + tile), e = __ldg(offsets + tile + 1);
+  const int cbase = (s >> 5) + tile;
+  jb.hbase = 2 * cbase + (by & 1) * ((e >> 5) + tile + 1 - cbase);
+  jb.x0 = tx * GAGS_TILE;
+  jb.y0 = by * 8;
+  jb.cfirst = ch0 + cblk * 128;
+  jb.cvalid = min(128, nch - cblk * 128);
+  return jb;
+}
+
 __global__ void __launch_bounds__(CB_THREADS, 2)
-blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
+blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, long long njobs,
                  const int *__restrict__ offsets, const unsigned char *__restrict__ wcache,
                  const int *__restrict__ wmeta, const int *__restrict__ wlist,
-                 const int *__restrict__ wcount, const float *__restrict__ v_render,
-                 float *__restrict__ v_colors) {
+                 const int *__restrict__ wcount, int *__restrict__ jobctr,
+                 const float *__restrict__ v_render, float *__restrict__ v_colors) {
   using L = CbLayout;
-  // blockIdx.x = tile column * nblk + channel block: the CTAs sharing a half tile's weight tiles
-  // are neighbours in launch order (their second read of a tile is an L2 hit)
-  const int tx = blockIdx.x / nblk, cblk = blockIdx.x - tx * nblk;
-  const int nbat = wcount[blockIdx.y * tile_w + tx];
-  if (nbat <= 0) return;
-  const int tile = (blockIdx.y >> 1) * tile_w + tx;
-  const int s = offsets[tile], e = offsets[tile + 1];
-  const int cbase = (s >> 5) + tile;
-  const int hbase = 2 * cbase + (int)(blockIdx.y & 1) * ((e >> 5) + tile + 1 - cbase);
-  const int cfirst = ch0 + cblk * 128;               // first channel of this CTA
-  const int cvalid = min(128, nch - cblk * 128);     // channels of this block that exist (% 16 == 0)
-
   // The kernel has no static shared memory, so the dynamic window starts at the CTA's shared-memory
   // base (1 KB aligned, which SWIZZLE_128B needs); the layout uses every byte of the two-CTAs-per-SM
   // budget, so this is checked instead of padded.
@@ -107,13 +129,8 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
   CbCtl &ctl = *reinterpret_cast<CbCtl *>(sm + L::CTL_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int x0 = tx * GAGS_TILE, y0 = blockIdx.y * 8;
 #ifdef GAGS_TC_TIMING
-  int dbg_slot = -1;
-  {
-    const int lin = blockIdx.y * gridDim.x + blockIdx.x, tot = gridDim.x * gridDim.y;
-    for (int k = 0; k < 8; ++k) if (lin == (tot / 9) * (k + 1)) dbg_slot = k;
-  }
+  int dbg_slot = (blockIdx.x % 37 == 5 && blockIdx.x / 37 < 8) ? (int)(blockIdx.x / 37) : -1;
   if (warp == 0) CB_STAMP(3, 0, 0);
 #endif
 
@@ -124,124 +141,163 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
       mbar_init(&ctl.accfull[k], 1);
       mbar_init(&ctl.accfree[k], 4);               // epilogue warps
     }
-    mbar_init(&ctl.vfull, 4);
+    mbar_init(&ctl.vfull, 4);                      // staging warps
+    mbar_init(&ctl.vfree, 1);                      // tcgen05.commit after a job's last MMA
+    for (int k = 0; k < CB_JQ; ++k) mbar_init(&ctl.jq_full[k], 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  if (warp == 9) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = ctl.tmem_base;
+  // k-th job id of this CTA as seen by a non-staging role (-1 = no more work)
+  auto next_job = [&](int k) -> long long {
+    mbar_wait_bounded(&ctl.jq_full[k & (CB_JQ - 1)], (uint32_t)((k / CB_JQ) & 1));
+    return (long long)*reinterpret_cast<volatile int *>(&ctl.jobq[k & (CB_JQ - 1)]);
+  };
 
   if (warp < 4) {
-    // ======================= v_render staging, then epilogue =======================================
-    const int q = warp;                             // TMEM lane quarter == warp % 4; pixel block
-    {
-      // the whole 64 KB block is in flight at once: 32 x 16-B loads per thread.
-      // lane -> 4 channels at 4 lane (first 16-B load) and 64 + 4 lane... keep 32-B granules:
-      // lane l owns channels [8 (l & 15), +8) of pixel row 2 j + (l >> 4)
-      const int n0 = (lane & 15) * 8;
-      const bool chan_ok = n0 < cvalid;
-      const uint32_t coff = (uint32_t)((n0 >> 6) & 1) * 16384u + (uint32_t)((n0 & 63) >> 3) * 16u;
-      unsigned char *vhi = sV, *vlo = sV + L::VPART;
-      float4 v[16][2];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int ql = 2 * j + (lane >> 4);         // pixel index inside this quarter's 8x4 block
-        const int xx = x0 + ((q & 1) << 3) + (ql & 7), yy = y0 + ((q >> 1) << 2) + (ql >> 3);
-        v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (chan_ok && xx < W && yy < H) {
-          const float4 *src = reinterpret_cast<const float4 *>(
-              v_render + ((size_t)yy * W + xx) * D + cfirst + n0);
-          v[j][0] = ldg_nc4(src);
-          v[j][1] = ldg_nc4(src + 1);
-        }
+    // ======================= v_render staging ======================================================
+    const int q = warp;                             // pixel block (8x4) of the half tile
+    const int n0 = (lane & 15) * 8;                 // lane l owns channels [8 (l & 15), +8) of pixel
+    const uint32_t coff = (uint32_t)((n0 >> 6) & 1) * 16384u + (uint32_t)((n0 & 63) >> 3) * 16u;
+    unsigned char *vhi = sV, *vlo = sV + L::VPART;
+    int jn = 0;                                     // non-empty jobs staged so far
+    for (int k = 0;; ++k) {
+      // fetch + publish the k-th job id (staging leads every other role)
+      if (tid == 0) {
+        const int got = atomicAdd(jobctr, 1);
+        ctl.jobq[k & (CB_JQ - 1)] = (long long)got < njobs ? got : -1;
+        __threadfence_block();
+        mbar_arrive(&ctl.jq_full[k & (CB_JQ - 1)]);
       }
+      named_bar_sync(3, 128);
+      const long long j = (long long)*reinterpret_cast<volatile int *>(&ctl.jobq[k & (CB_JQ - 1)]);
+      if (j < 0) break;
+      const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
+      if (jb.nbat <= 0) continue;
+      const bool chan_ok = n0 < jb.cvalid;
+      const float *vbase = v_render + jb.cfirst + n0;
+      // first half of the loads may fly before the previous job's MMAs have released the buffer
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {
+        float4 v[8][2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = q * 32 + 2 * j + (lane >> 4); // row of the K = 128 px dimension
-        uint4 h, l;
-        split_pack2(v[j][0].x, v[j][0].y, h.x, l.x);
-        split_pack2(v[j][0].z, v[j][0].w, h.y, l.y);
-        split_pack2(v[j][1].x, v[j][1].y, h.z, l.z);
-        split_pack2(v[j][1].z, v[j][1].w, h.w, l.w);
-        const uint32_t off = (uint32_t)(r >> 3) * 1024u +
-                             sw128((uint32_t)(r & 7) * 128u + (coff & 127u)) + (coff & ~127u);
-        *reinterpret_cast<uint4 *>(vhi + off) = h;
-        *reinterpret_cast<uint4 *>(vlo + off) = l;
+        for (int jj = 0; jj < 8; ++jj) {
+          const int ql = 2 * (round * 8 + jj) + (lane >> 4);   // pixel inside this 8x4 block
+          const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+          v[jj][0] = v[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (chan_ok && xx < W && yy < H) {
+            const float4 *src = reinterpret_cast<const float4 *>(vbase + ((size_t)yy * W + xx) * D);
+            v[jj][0] = ldg_nc4(src);
+            v[jj][1] = ldg_nc4(src + 1);
+          }
+        }
+        if (round == 0 && jn > 0) mbar_wait_bounded(&ctl.vfree, (uint32_t)((jn - 1) & 1));
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int r = q * 32 + 2 * (round * 8 + jj) + (lane >> 4);   // row of the K = 128 px dim
+          uint4 h, l;
+          split_pack2(v[jj][0].x, v[jj][0].y, h.x, l.x);
+          split_pack2(v[jj][0].z, v[jj][0].w, h.y, l.y);
+          split_pack2(v[jj][1].x, v[jj][1].y, h.z, l.z);
+          split_pack2(v[jj][1].z, v[jj][1].w, h.w, l.w);
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u +
+                               sw128((uint32_t)(r & 7) * 128u + (coff & 127u)) + (coff & ~127u);
+          *reinterpret_cast<uint4 *>(vhi + off) = h;
+          *reinterpret_cast<uint4 *>(vlo + off) = l;
+        }
       }
       fence_async_smem();
       mbar_arrive_warp(&ctl.vfull);
-      if (warp == 0) CB_STAMP(3, 0, 1);
+      if (warp == 0 && jn < 2) CB_STAMP(3, 0, 1 + jn);
+      ++jn;
     }
-    // Epilogue: the four warps are the four TMEM lane quarters = 128 channels.  Per step: TMEM ->
-    // registers -> [16 g][128 ch] fp32 in shared memory (two passes) -> one bulk async reduction
+  } else if (warp < 8) {
+    // ======================= epilogue ==============================================================
+    // The four warps are the four TMEM lane quarters = 128 channels.  Per step: TMEM -> registers ->
+    // [16 g][128 ch] fp32 in shared memory (two halves, two buffers) -> one bulk async reduction
     // (TMA add at L2) per Gaussian row, 512 B contiguous.
+    const int q = warp - 4;                         // == warp % 4
     float *stg0 = reinterpret_cast<float *>(sm + L::STG_OFF);
-    for (int gi = 0; gi < nbat; ++gi) {
-      const int buf = gi & 1;
-      // Gaussian row this lane reduces into (warp 0 issues): straight from the cached ids
-      int gid = -1;
-      if (warp == 0) {
-        const int slot = hbase + __ldg(wlist + hbase + gi);
-        gid = __ldg(wmeta + (size_t)slot * TC_KB + lane);
-      }
-      if (warp == 0) CB_STAMP(0, gi, 0);
-      mbar_wait_bounded(&ctl.accfull[buf], (gi >> 1) & 1);
-      tc_fence_after();
-      if (warp == 0) CB_STAMP(0, gi, 1);
-      float acc[32];
-      {
-        uint32_t ra[32], rb[32];
-        const uint32_t ta = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
-        tmem_ld_32x32(ta, ra);
-        tmem_ld_32x32(ta + 32, rb);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
-      }
-      tc_fence_before();
-      mbar_arrive_warp(&ctl.accfree[buf]);
-      if (warp == 0) CB_STAMP(0, gi, 2);
-      // a survivor that reached no pixel of the half tile has an exactly-zero row: no reduction
-      // (fp32 reductions top out at ~2.95 TB/s chip-wide on B200 — tools/red_rate.cu — which makes
-      // them this kernel's floor, so every skipped row counts)
-      uint32_t nz = 0;
-#pragma unroll
-      for (int g = 0; g < 32; ++g) nz |= __any_sync(0xffffffffu, acc[g] != 0.f) ? (1u << g) : 0u;
-      // two staging buffers, one per half: the bulk reductions of one half drain (TMA reads shared
-      // memory at the L2 reduction rate) while the other half and the next step are produced
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float *stg = stg0 + half * 2048;
-        if (warp == 0) bulk_wait_read1();            // this buffer's previous reductions have left smem
-        named_bar_sync(2, 128);
-#pragma unroll
-        for (int g = 0; g < 16; ++g) stg[g * 128 + q * 32 + lane] = acc[half * 16 + g];
-        if (lane == 0) ctl.nzmask[half][q] = nz;
-        fence_async_smem();
-        named_bar_sync(2, 128);
-        if (warp == 0) {
-          const uint32_t any = ctl.nzmask[half][0] | ctl.nzmask[half][1] | ctl.nzmask[half][2] |
-                               ctl.nzmask[half][3];
-          const int g = lane - half * 16;            // lanes [16 half, 16 half + 16) issue
-          if (g >= 0 && g < 16 && gid >= 0 && cvalid > 0 && ((any >> lane) & 1u))
-            bulk_red_add_f32(v_colors + (size_t)gid * D + cfirst, stg + g * 128, (uint32_t)cvalid * 4u);
-          bulk_commit();
+    int gs = 0;                                     // global step counter of this CTA
+    for (int k = 0;; ++k) {
+      const long long j = next_job(k);
+      if (j < 0) break;
+      const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
+      for (int gi = 0; gi < jb.nbat; ++gi, ++gs) {
+        const int buf = gs & 1;
+        // Gaussian row this lane reduces into (warp 4 issues): straight from the cached ids
+        int gid = -1;
+        if (q == 0) {
+          const int slot = jb.hbase + __ldg(wlist + jb.hbase + gi);
+          gid = __ldg(wmeta + (size_t)slot * TC_KB + lane);
         }
+        if (q == 0 && gs < 16) CB_STAMP(0, gs, 0);
+        mbar_wait_bounded(&ctl.accfull[buf], (uint32_t)((gs >> 1) & 1));
+        tc_fence_after();
+        if (q == 0 && gs < 16) CB_STAMP(0, gs, 1);
+        float acc[32];
+        {
+          uint32_t ra[32], rb[32];
+          const uint32_t ta = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
+          tmem_ld_32x32(ta, ra);
+          tmem_ld_32x32(ta + 32, rb);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
+        }
+        tc_fence_before();
+        mbar_arrive_warp(&ctl.accfree[buf]);
+        if (q == 0 && gs < 16) CB_STAMP(0, gs, 2);
+        // a survivor that reached no pixel of the half tile has an exactly-zero row: no reduction
+        // (fp32 reductions top out at ~2.95 TB/s chip-wide on B200 — tools/red_rate.cu — which
+        // makes them this kernel's floor, so every skipped row counts)
+        uint32_t nz = 0;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) nz |= __any_sync(0xffffffffu, acc[g] != 0.f) ? (1u << g) : 0u;
+        // two staging buffers, one per half: the bulk reductions of one half drain (TMA reads
+        // shared memory at the L2 reduction rate) while the other half and the next step are produced
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float *stg = stg0 + half * 2048;
+          if (q == 0) bulk_wait_read1();            // this buffer's previous reductions left smem
+          named_bar_sync(2, 128);
+#pragma unroll
+          for (int g = 0; g < 16; ++g) stg[g * 128 + q * 32 + lane] = acc[half * 16 + g];
+          if (lane == 0) ctl.nzmask[half][q] = nz;
+          fence_async_smem();
+          named_bar_sync(2, 128);
+          if (q == 0) {
+            const uint32_t any = ctl.nzmask[half][0] | ctl.nzmask[half][1] | ctl.nzmask[half][2] |
+                                 ctl.nzmask[half][3];
+            const int g = lane - half * 16;          // lanes [16 half, 16 half + 16) issue
+            if (g >= 0 && g < 16 && gid >= 0 && jb.cvalid > 0 && ((any >> lane) & 1u))
+              bulk_red_add_f32(v_colors + (size_t)gid * D + jb.cfirst, stg + g * 128,
+                               (uint32_t)jb.cvalid * 4u);
+            bulk_commit();
+          }
+        }
+        if (q == 0 && gs < 16) CB_STAMP(0, gs, 3);
       }
-      if (warp == 0) CB_STAMP(0, gi, 3);
     }
-    if (warp == 0) bulk_wait_read0();                // shared memory must outlive the last reads
-  } else if (warp == 4) {
+    if (q == 0) bulk_wait_read0();                   // shared memory must outlive the last reads
+  } else if (warp == 8) {
     // ======================= bulk-copy producer: one cached weight tile per step ====================
     if (lane == 0) {
-      for (int gi = 0; gi < nbat; ++gi) {
-        const int st = gi & 1;
-        if (gi >= 2) mbar_wait_bounded(&ctl.wfree[st], ((gi >> 1) - 1) & 1);
-        CB_STAMP(1, gi, 0);
-        mbar_expect_tx(&ctl.wfull[st], 16384u);
-        const int slot = hbase + __ldg(wlist + hbase + gi);
-        bulk_g2s(sW + st * 16384, wcache + (size_t)slot * 16384, 16384u, &ctl.wfull[st]);
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        const long long j = next_job(k);
+        if (j < 0) break;
+        const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
+        for (int gi = 0; gi < jb.nbat; ++gi, ++gs) {
+          const int st = gs & 1;
+          if (gs >= 2) mbar_wait_bounded(&ctl.wfree[st], (uint32_t)(((gs >> 1) - 1) & 1));
+          if (gs < 16) CB_STAMP(1, gs, 0);
+          mbar_expect_tx(&ctl.wfull[st], 16384u);
+          const int slot = jb.hbase + __ldg(wlist + jb.hbase + gi);
+          bulk_g2s(sW + st * 16384, wcache + (size_t)slot * 16384, 16384u, &ctl.wfull[st]);
+        }
       }
     }
     __syncwarp();
@@ -251,26 +307,35 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
       const uint32_t idesc = umma_idesc_bf16(64, true, true);
       const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 16384, 1024);
       const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW), 16, 1024);
-      mbar_wait_bounded(&ctl.vfull, 0);
-      for (int gi = 0; gi < nbat; ++gi) {
-        const int st = gi & 1, buf = gi & 1;
-        CB_STAMP(2, gi, 0);
-        mbar_wait_bounded(&ctl.wfull[st], (gi >> 1) & 1);
-        CB_STAMP(2, gi, 1);
-        if (gi >= 2) mbar_wait_bounded(&ctl.accfree[buf], ((gi >> 1) - 1) & 1);
-        tc_fence_after();
-        CB_STAMP(2, gi, 2);
-        const uint32_t d = tb + (uint32_t)(buf * 64);
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ahi = v_desc0 + (uint64_t)((ks * 2048) >> 4);
-          const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
-          const uint64_t bw = w_desc0 + (uint64_t)((st * 16384 + ks * 2048) >> 4);
-          umma_bf16_ss(d, ahi, bw, idesc, ks > 0 ? 1u : 0u);
-          umma_bf16_ss(d, alo, bw, idesc, 1u);
+      int gs = 0, jn = 0;
+      for (int k = 0;; ++k) {
+        const long long j = next_job(k);
+        if (j < 0) break;
+        const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
+        if (jb.nbat <= 0) continue;
+        mbar_wait_bounded(&ctl.vfull, (uint32_t)(jn & 1));
+        for (int gi = 0; gi < jb.nbat; ++gi, ++gs) {
+          const int st = gs & 1, buf = gs & 1;
+          if (gs < 16) CB_STAMP(2, gs, 0);
+          mbar_wait_bounded(&ctl.wfull[st], (uint32_t)((gs >> 1) & 1));
+          if (gs < 16) CB_STAMP(2, gs, 1);
+          if (gs >= 2) mbar_wait_bounded(&ctl.accfree[buf], (uint32_t)(((gs >> 1) - 1) & 1));
+          tc_fence_after();
+          if (gs < 16) CB_STAMP(2, gs, 2);
+          const uint32_t d = tb + (uint32_t)(buf * 64);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ahi = v_desc0 + (uint64_t)((ks * 2048) >> 4);
+            const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
+            const uint64_t bw = w_desc0 + (uint64_t)((st * 16384 + ks * 2048) >> 4);
+            umma_bf16_ss(d, ahi, bw, idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, alo, bw, idesc, 1u);
+          }
+          umma_commit(&ctl.wfree[st]);
+          umma_commit(&ctl.accfull[buf]);
+          if (gs < 16) CB_STAMP(2, gs, 3);
         }
-        umma_commit(&ctl.wfree[st]);
-        umma_commit(&ctl.accfull[buf]);
-        CB_STAMP(2, gi, 3);
+        umma_commit(&ctl.vfree);                     // the v_render block may be overwritten
+        ++jn;
       }
     }
     __syncwarp();
@@ -278,12 +343,12 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) CB_STAMP(3, 0, 2);
-  if (warp == 5) tmem_dealloc<L::TCOLS>(tb);
+  if (warp == 0) CB_STAMP(3, 0, 3);
+  if (warp == 9) tmem_dealloc<L::TCOLS>(tb);
 }
 
 int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const unsigned char *wcache,
-              const int *wmeta, const int *wlist, const int *wcount, const float *v_render,
+              const int *wmeta, const int *wlist, int *wcount, const float *v_render,
               float *v_colors, cudaStream_t st) {
   using L = CbLayout;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
@@ -296,8 +361,16 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  blend_bwd_cached<<<dim3(tw * nblk, hh), CB_THREADS, L::BYTES, st>>>(
-      D, ch0, nch, nblk, W, H, tw, offsets, wcache, wmeta, wlist, wcount, v_render, v_colors);
+  const long long njobs = (long long)tw * nblk * hh;
+  if (njobs > 0x7fffffffLL - 4096) return GAGS_ERANGE;
+  const long long want = 2LL * 148;                  // two persistent CTAs per SM
+  const unsigned grid = (unsigned)(njobs < want ? njobs : want);
+  int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
+  cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  blend_bwd_cached<<<grid, CB_THREADS, L::BYTES, st>>>(
+      D, ch0, nch, nblk, W, H, tw, njobs, offsets, wcache, wmeta, wlist, wcount, jobctr, v_render,
+      v_colors);
   return (int)cudaGetLastError();
 }
 
@@ -306,7 +379,7 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
 extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
                                               const int32_t *offsets, const void *wcache,
                                               const int32_t *wmeta, const int32_t *wlist,
-                                              const int32_t *wcount, const float *v_render,
+                                              int32_t *wcount, const float *v_render,
                                               float *v_colors, void *stream) {
   if (!offsets || !wcache || !wmeta || !wlist || !wcount || !v_render || !v_colors) return GAGS_EINVAL;
   if (D <= 32 || D % 16 != 0 || width <= 0 || height <= 0) return GAGS_EINVAL;

@@ -250,3 +250,13 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   }
   return 0;
 }
+
+// Zero-fill through cudaMemsetAsync (a driver memset, not one of this library's kernels): used for
+// the 2 GB gradient accumulation buffer so that the fill does not compete for SM slots with the
+// kernels running on the other stream.
+extern "C" int gags_memset_zero(void *ptr, size_t bytes, void *stream) {
+  if (!ptr && bytes) return GAGS_EINVAL;
+  if (bytes == 0) return 0;
+  GAGS_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+  return 0;
+}

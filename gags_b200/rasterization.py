@@ -41,12 +41,12 @@ class _CacheLease:
     def __init__(self, dev, slots: int, n_half: int):
         key = (dev.type, dev.index)
         bufs = _cache_pool.pop(key, None)
-        if bufs is None or bufs[2].numel() < slots or bufs[3].numel() < n_half:
+        if bufs is None or bufs[2].numel() < slots or bufs[3].numel() < n_half + 1:
             cap = int(slots * 1.25) + 1024
             bufs = (torch.empty(cap * 16384, dtype=torch.uint8, device=dev),
                     torch.empty(cap * 32, dtype=torch.int32, device=dev),
                     torch.empty(cap, dtype=torch.int32, device=dev),
-                    torch.empty(max(n_half, 1), dtype=torch.int32, device=dev))
+                    torch.empty(n_half + 1, dtype=torch.int32, device=dev))
         self.key, self.bufs = key, bufs
 
     def __del__(self):
@@ -275,8 +275,11 @@ bucket_sort = False
 
 
 @torch.no_grad()
-def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int) -> Dict:
-    """tiles_touched -> scan -> emit -> stable radix sort -> offsets.  One host sync (n_isects)."""
+def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int,
+                 after_count=None) -> Dict:
+    """tiles_touched -> scan -> emit -> stable radix sort -> offsets.  One host sync (n_isects).
+    `after_count()` (optional) runs on the host right after that readback, before the emit / sort
+    kernels are enqueued (the lookahead uses it to order them behind the main stream)."""
     N = radii.shape[0]
     dev = radii.device
     st = _C.stream_ptr()
@@ -292,6 +295,9 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
                  "gags_tile_bucket_count")
         _C.count_launch(2)
         n, max_bucket = (int(v) for v in stats.tolist())      # the one host sync of the pipeline
+        if after_count is not None:
+            after_count()
+            after_count = None
         if max_bucket <= _C.lib.gags_tile_bucket_max():
             if n > _isect_capacity:
                 _isect_capacity = int(n * 1.2) + 1024
@@ -316,6 +322,8 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
                                    _C.ptr(ws), ws_bytes, st), "gags_tile_scan")
     _C.count_launch(2)
     n = int(n_dev.item())                     # the one host sync of the pipeline
+    if after_count is not None:
+        after_count()
     n_tiles = tile_w * tile_h
     # n varies by a few percent from view to view; allocating a grow-only capacity instead keeps
     # every view's request the same size, so the caching allocator recycles blocks instead of
@@ -398,7 +406,9 @@ class _Blend(torch.autograd.Function):
             main = torch.cuda.current_stream(dev)
             side = _side_state(dev)["stream"]
             with torch.cuda.stream(side):
-                vz = torch.zeros(N, D, dtype=torch.float32, device=dev)
+                vz = torch.empty(N, D, dtype=torch.float32, device=dev)
+                _C.check(_C.lib.gags_memset_zero(_C.ptr(vz), vz.numel() * 4, _C.stream_ptr()),
+                         "gags_memset_zero")
                 evz = torch.cuda.Event()
                 evz.record(side)
             ctx.prezero = (vz, evz, main)
@@ -494,7 +504,13 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
                                     far_plane, radius_clip, scaling_modifier, flags)
             radii, means2d, depths, conics, opac, tiles, geom = _Project.apply(
                 means, quats, scales, opacities, cam, keep, tile_w, tile_h)
-            binned = bin_and_sort(means2d, radii, depths, tiles, tile_w, tile_h)
+            # Projection, the scan and the n_isects readback run early (beside the previous view's
+            # loss / backward): the host is not held up behind the main stream's queue.  The emit /
+            # sort kernels are then ordered behind everything the main stream has queued by now (up
+            # to the optimiser pass): measured (tools/trace_step.py), a sort that is runnable while
+            # Adam streams costs Adam 0.5 ms, and beside the persistent backward it cannot get an SM.
+            binned = bin_and_sort(means2d, radii, depths, tiles, tile_w, tile_h,
+                                  after_count=lambda: side.wait_stream(main))
             ev = torch.cuda.Event()
             ev.record(side)
         main.wait_event(ev)

@@ -177,7 +177,8 @@ int gags_blend_bwd_features(const float *geom, int32_t D, int32_t width, int32_t
  * GEMM over those tiles instead of re-walking the tile lists (same result as
  * gags_blend_bwd_features).  Caller-owned buffers, `slots = gags_blend_cache_slots(n_isects,
  * n_tiles)`:  wcache[slots * 16384] bytes (16-B aligned), wmeta[slots * 32], wlist[slots],
- * wcount[tile_w * ceil(height / 8)].  None needs initialising.                                 */
+ * wcount[tile_w * ceil(height / 8) + 1] (the extra int is the backward's job counter).  None needs
+ * initialising.                                                                                */
 int gags_blend_cache_supported(int32_t D);     /* 1 if the cached pair handles this D          */
 int64_t gags_blend_cache_slots(int64_t n_isects, int32_t n_tiles);
 int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
@@ -188,7 +189,7 @@ int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
 int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
                                    const int32_t *offsets, const void *wcache,
                                    const int32_t *wmeta, const int32_t *wlist,
-                                   const int32_t *wcount, const float *v_render, float *v_colors,
+                                   int32_t *wcount, const float *v_render, float *v_colors,
                                    void *stream);
 
 /* K8b full backward (replaces rasterize_to_pixels_bwd; App. A.6).  Outputs must be
@@ -229,6 +230,10 @@ int gags_scale_inplace(float *v, const float *scale_dev, int64_t numel, void *st
 int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t numel,
                    double lr, double beta1, double beta2, double eps, int32_t step,
                    int32_t zero_grad, void *stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (driver memset; keeps the 2 GB gradient-buffer fill off
+ * the SMs that the neighbouring stream's kernels need). */
+int gags_memset_zero(void *ptr, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }

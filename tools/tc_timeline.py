@@ -38,7 +38,8 @@ for slot in range(8):
     t0 = int(tbw[slot, 3, 0, 0])
     if t0 == 0:
         continue
-    print(f"=== bwd CTA slot {slot}: vfull +{int(tbw[slot,3,0,1])-t0}, end +{int(tbw[slot,3,0,2])-t0}")
+    print(f"=== bwd CTA slot {slot} (persistent; steps run across jobs): vfull job0 +{int(tbw[slot,3,0,1])-t0}, "
+          f"vfull job1 +{int(tbw[slot,3,0,2])-t0}, CTA end +{int(tbw[slot,3,0,3])-t0}")
     for b in range(16):
         if tbw[slot, 2, b, 0] == 0:
             break
