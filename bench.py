@@ -176,6 +176,9 @@ def main():
     # emb[seg] on the fly (the reference materialises the dense map every iteration, train.py:162)
     targets_dev = [(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
 
+    # k views per optimiser step: let the backward reduce straight into .grad (see rasterization.py)
+    R.direct_grad_accumulation = kviews > 1
+
     def one_view(cam, target):
         pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
         loss = l1_loss_segmap_fused(pkg["render"], target[0], target[1])

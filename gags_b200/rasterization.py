@@ -24,6 +24,14 @@ from . import _C
 
 TILE = 16
 
+# Multi-view gradient accumulation (view-parallel training renders k views per optimiser step):
+# when the colours ARE a leaf parameter, the feature backward can reduce straight into its .grad
+# instead of into a fresh zeroed [N, D] buffer that autograd then adds to .grad (a 2 GB fill + a
+# 6 GB read-modify-write per extra view at config 3).  Same arithmetic as AccumulateGrad's `+=`;
+# what it skips are tensor / AccumulateGrad hooks on that parameter, hence opt-in
+# (parallel.allreduce_grads does not use hooks).
+direct_grad_accumulation = False
+
 # Keep the forward's blend-weight tiles for the feature backward (training with frozen geometry).
 # The parity tests switch it off to exercise the recomputing backward kernels as well.
 weight_cache = True
@@ -367,6 +375,10 @@ class _Blend(torch.autograd.Function):
     def forward(ctx, means2d, conics, opac, colors, background, geom, offsets, flatten_ids,
                 width, height):
         _C.require_cuda(colors, geom)
+        ctx.sink = None
+        if (direct_grad_accumulation and colors.is_leaf and colors.requires_grad
+                and colors.dtype == torch.float32 and colors.is_contiguous()):
+            ctx.sink = colors
         colors = _f32c(colors)
         N, D = colors.shape
         dev = colors.device
@@ -430,7 +442,12 @@ class _Blend(torch.autograd.Function):
         v_render = _f32c(v_render)
         st = _C.stream_ptr()
         _mark("bwd_start")
-        if need_col and ctx.prezero is not None:
+        sink = ctx.sink if (need_col and not need_geo) else None
+        if sink is not None and sink.grad is not None and sink.grad.is_contiguous() \
+                and sink.grad.dtype == torch.float32:
+            v_colors = sink.grad                     # accumulate in place: nothing to zero or add
+            ctx.prezero = None
+        elif need_col and ctx.prezero is not None:
             v_colors, evz, _ = ctx.prezero
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(evz)
@@ -468,6 +485,10 @@ class _Blend(torch.autograd.Function):
         _mark("blend_bwd")
         if ctx.needs_input_grad[4] and bg is not None:
             v_bg = (v_render * (1.0 - alphas)[..., None]).sum(dim=(0, 1))
+        if sink is not None:
+            if sink.grad is None:
+                sink.grad = v_colors                 # first view of the step: adopt the buffer
+            v_colors = None                          # already accumulated; nothing for autograd to add
         return v_m, v_c, v_o, v_colors, v_bg, None, None, None, None, None
 
 

@@ -468,6 +468,30 @@ def test_geometry_gradients_end_to_end_rgb():
     assert pkg["viewspace_points"].grad is not None
 
 
+def test_direct_grad_accumulation_equals_autograd():
+    """two views accumulated into one .grad: reducing in place == fresh buffer + autograd's `+=`."""
+    from gags_b200 import rasterization as R
+    W, H, D = 80, 56, 64
+    sc = front_scene(700, W, H, D, seed=77)
+    st = _stages(sc)
+    g = torch.Generator().manual_seed(4)
+    v1, v2 = torch.randn(H, W, D, generator=g).cuda(), torch.randn(H, W, D, generator=g).cuda()
+    grads = []
+    try:
+        for direct in (False, True):
+            R.direct_grad_accumulation = direct
+            col = torch.nn.Parameter(sc["colors"].cuda())
+            for v in (v1, v2):
+                out, _, _ = R._Blend.apply(st["means2d"], st["conics"], st["opac"], col, None,
+                                           st["geom"], st["offsets"], st["flatten_ids"], W, H)
+                (out * v).sum().backward()
+            torch.cuda.synchronize()
+            grads.append(col.grad.clone())
+    finally:
+        R.direct_grad_accumulation = False
+    assert rel_err(grads[1], grads[0]) < 2e-6
+
+
 def test_fused_l1_chains_grad_output():
     """the fused L1's stored gradient is scaled on the device by whatever autograd sends in."""
     from gags_b200.utils.loss_utils import l1_loss, l1_loss_fused
