@@ -52,7 +52,6 @@ struct CbCtl {
   uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull, vfree;
   uint64_t jq_full[CB_JQ];
   uint32_t tmem_base;
-  uint32_t nzmask[2][4];      // per staging buffer and epilogue warp: Gaussians with a non-zero row
   int jobq[CB_JQ];
 };
 
@@ -68,25 +67,12 @@ struct CbLayout {
   static constexpr int VPART = 32768;                  // one bf16 part (hi or lo): 128 px x 128 ch
   static constexpr int V_OFF = 0;
   static constexpr int W_OFF = 2 * VPART;              // 2 stages x one 16 KB weight tile
-  static constexpr int STG_OFF = W_OFF + 32768;        // 2 x [16 g][128 ch] fp32
+  static constexpr int STG_OFF = W_OFF + 32768;        // 4 epilogue warps x [32 g][32 ch] fp32
   static constexpr int CTL_OFF = STG_OFF + 16384;
   static constexpr int BYTES = CTL_OFF + (int)sizeof(CbCtl);   // no slack: base must be 1 KB aligned
   static constexpr int TCOLS = 128;                    // 2 accumulator buffers x [hi(32) | lo(32)]
 };
 static_assert(CbLayout::BYTES <= (233472 / 2 - 1024), "cached backward must fit twice per SM");
-
-// shared -> global bulk async REDUCTION (TMA, fp32 add performed at L2): one op per Gaussian row
-__device__ __forceinline__ void bulk_red_add_f32(float *gdst, const void *ssrc, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read1() {
-  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-}
 
 // what every role needs to know about a job; all roles enumerate the jobs identically
 struct CbJob {
@@ -217,10 +203,9 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
   } else if (warp < 8) {
     // ======================= epilogue ==============================================================
     // The four warps are the four TMEM lane quarters = 128 channels.  Per step: TMEM -> registers ->
-    // [16 g][128 ch] fp32 in shared memory (two halves, two buffers) -> one bulk async reduction
-    // (TMA add at L2) per Gaussian row, 512 B contiguous.
+    // per-warp transpose -> 16-byte vector reds.
     const int q = warp - 4;                         // == warp % 4
-    float *stg0 = reinterpret_cast<float *>(sm + L::STG_OFF);
+    float *stg = reinterpret_cast<float *>(sm + L::STG_OFF + q * 4096);
     int gs = 0;                                     // global step counter of this CTA
     for (int k = 0;; ++k) {
       const long long j = next_job(k);
@@ -228,12 +213,10 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
       const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
       for (int gi = 0; gi < jb.nbat; ++gi, ++gs) {
         const int buf = gs & 1;
-        // Gaussian row this lane reduces into (warp 4 issues): straight from the cached ids
-        int gid = -1;
-        if (q == 0) {
-          const int slot = jb.hbase + __ldg(wlist + jb.hbase + gi);
-          gid = __ldg(wmeta + (size_t)slot * TC_KB + lane);
-        }
+        // Gaussian ids of the tile's 32 rows (lane g holds row g's id): straight from the cache,
+        // issued before the wait so the latency hides behind the MMAs
+        const int slot = jb.hbase + __ldg(wlist + jb.hbase + gi);
+        const int gid_l = __ldg(wmeta + (size_t)slot * TC_KB + lane);
         if (q == 0 && gs < 16) CB_STAMP(0, gs, 0);
         mbar_wait_bounded(&ctl.accfull[buf], (uint32_t)((gs >> 1) & 1));
         tc_fence_after();
@@ -250,38 +233,31 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
         tc_fence_before();
         mbar_arrive_warp(&ctl.accfree[buf]);
         if (q == 0 && gs < 16) CB_STAMP(0, gs, 2);
-        // a survivor that reached no pixel of the half tile has an exactly-zero row: no reduction
-        // (fp32 reductions top out at ~2.95 TB/s chip-wide on B200 — tools/red_rate.cu — which
-        // makes them this kernel's floor, so every skipped row counts)
-        uint32_t nz = 0;
+        // Reductions: per-warp transpose through 4 KB of shared memory (lane = channel ->
+        // lane = 4 channels of one of 4 rows), then 16-byte vector reds, 128 contiguous bytes per
+        // Gaussian row and warp, fire-and-forget.  What bounds them (tools/red_rate.cu and the
+        // timelines in profiles/): a warp sustains only so many red INSTRUCTIONS in flight, so
+        // scalar reds from registers ran at 0.8 B/cycle/warp and v4 reds at ~3.5; shared-memory
+        // staged TMA bulk reductions were limited by the staging buffers they pin (2 x 8 KB in
+        // flight per CTA).  Chip-wide the rate tops out near 3 TB/s for distinct rows (each first
+        // touch of a line is a DRAM read-modify-write) and 5+ TB/s when rows repeat in L2.
+        // A survivor that reached no pixel of the half tile has an exactly-zero row: skipped.
 #pragma unroll
-        for (int g = 0; g < 32; ++g) nz |= __any_sync(0xffffffffu, acc[g] != 0.f) ? (1u << g) : 0u;
-        // two staging buffers, one per half: the bulk reductions of one half drain (TMA reads
-        // shared memory at the L2 reduction rate) while the other half and the next step are produced
+        for (int g = 0; g < 32; ++g) stg[g * 32 + lane] = acc[g];
+        __syncwarp();
+        const int cb = q * 32 + (lane & 7) * 4;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float *stg = stg0 + half * 2048;
-          if (q == 0) bulk_wait_read1();            // this buffer's previous reductions left smem
-          named_bar_sync(2, 128);
-#pragma unroll
-          for (int g = 0; g < 16; ++g) stg[g * 128 + q * 32 + lane] = acc[half * 16 + g];
-          if (lane == 0) ctl.nzmask[half][q] = nz;
-          fence_async_smem();
-          named_bar_sync(2, 128);
-          if (q == 0) {
-            const uint32_t any = ctl.nzmask[half][0] | ctl.nzmask[half][1] | ctl.nzmask[half][2] |
-                                 ctl.nzmask[half][3];
-            const int g = lane - half * 16;          // lanes [16 half, 16 half + 16) issue
-            if (g >= 0 && g < 16 && gid >= 0 && jb.cvalid > 0 && ((any >> lane) & 1u))
-              bulk_red_add_f32(v_colors + (size_t)gid * D + jb.cfirst, stg + g * 128,
-                               (uint32_t)jb.cvalid * 4u);
-            bulk_commit();
-          }
+        for (int it = 0; it < 8; ++it) {
+          const int g = it * 4 + (lane >> 3);
+          const float4 v = *reinterpret_cast<const float4 *>(stg + g * 32 + (lane & 7) * 4);
+          const int gg = __shfl_sync(0xffffffffu, gid_l, g);
+          if (gg >= 0 && cb < jb.cvalid && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+            red_add4(v_colors + (size_t)gg * D + jb.cfirst + cb, v);
         }
+        __syncwarp();
         if (q == 0 && gs < 16) CB_STAMP(0, gs, 3);
       }
     }
-    if (q == 0) bulk_wait_read0();                   // shared memory must outlive the last reads
   } else if (warp == 8) {
     // ======================= bulk-copy producer: one cached weight tile per step ====================
     if (lane == 0) {
