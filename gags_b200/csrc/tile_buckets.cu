@@ -7,14 +7,15 @@
 // ascending Gaussian index, i.e. inside a tile: ascending depth bits, ties by ascending Gaussian
 // index.  A Gaussian meets a tile at most once, so (depth_bits, gaussian) is a unique key inside a
 // tile and the same order is obtained without any global sort:
-//   1. tile_hist     count[t] += 1 for every (Gaussian, tile) pair            (L2 atomics)
-//   2. bucket_scan   offsets[t] = exclusive sum  -> this IS isect_offsets; n_isects and the largest
-//                    bucket come out as two extra ints (one host readback, as before)
-//   3. tile_scatter  slot = offsets[t] + cursor[t]++ ; bucket[slot] = depth_bits << gbits | gaussian
-//   4. bucket_sort   one CTA per tile: cub::BlockRadixSort of the tile's keys in shared memory,
-//                    write flatten_ids (and isect_ids for the caller's info dict)
-// HBM traffic: 24 B/Gaussian twice + 8 B/intersection written, read, then 12 B written — about a
-// fifth of the 6-pass global radix sort.  Buckets larger than BUCKET_MAX make the caller fall back
+//   1. tile_scatter  slot = cursor[t]++ (L2 atomic) ; bucket[t][slot] = (depth bits, gaussian) — a
+//                    fixed-capacity slab per tile, so no histogram pass has to come first
+//   2. bucket_scan   offsets[t] = exclusive sum of the counts -> this IS isect_offsets; n_isects and
+//                    the largest bucket come out as two extra ints (one host readback, as before)
+//   3. bucket_sort   one CTA per tile: cub::BlockRadixSort of (32-bit depth key, Gaussian value) in
+//                    shared memory, 6 passes of 6 bits, then runs of bit-identical depths are put
+//                    in Gaussian order; writes flatten_ids (and isect_ids for the info dict)
+// HBM traffic: 24 B/Gaussian + 8 B/intersection written, read, then 12 B written — about a sixth
+// of the 6-pass global radix sort.  Buckets larger than BUCKET_MAX make the caller fall back
 // to the global path.
 #include "common.cuh"
 #include <cub/block/block_radix_sort.cuh>
@@ -57,11 +58,19 @@ __device__ __forceinline__ void for_each_tile(const float2 *__restrict__ means2d
   }
 }
 
+// steps 1+3 fused: slot = cursor[t]++ ; the tile's bucket is the fixed-capacity slab
+// bucket[t * BUCKET_MAX ...] (entries beyond the capacity are dropped; the caller sees the count and
+// falls back to the global sort), so no histogram pass is needed before the scatter
 __global__ void __launch_bounds__(256)
-tile_hist_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii, long long N,
-                 int tile_w, int tile_h, int *__restrict__ count) {
-  for_each_tile(means2d, radii, N, tile_w, tile_h,
-                [&](int t, long long) { atomicAdd(count + t, 1); });
+tile_scatter_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii,
+                    const float *__restrict__ depths, long long N, int tile_w, int tile_h,
+                    int *__restrict__ cursor, uint2 *__restrict__ bucket) {
+  for_each_tile(means2d, radii, N, tile_w, tile_h, [&](int t, long long gid) {
+    const int slot = atomicAdd(cursor + t, 1);
+    if (slot < BUCKET_MAX)
+      bucket[(size_t)t * BUCKET_MAX + slot] =
+          make_uint2(__float_as_uint(__ldg(depths + gid)), (unsigned)gid);
+  });
 }
 
 // single CTA: exclusive scan of count[n_tiles] -> offsets[n_tiles + 1]; stats = {n_isects, max}
@@ -95,80 +104,113 @@ bucket_scan_kernel(const int *__restrict__ count, int n_tiles, int *__restrict__
   }
 }
 
-__global__ void __launch_bounds__(256)
-tile_scatter_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii,
-                    const float *__restrict__ depths, long long N, int tile_w, int tile_h,
-                    int gbits, const int *__restrict__ offsets, int *__restrict__ cursor,
-                    unsigned long long *__restrict__ bucket) {
-  for_each_tile(means2d, radii, N, tile_w, tile_h, [&](int t, long long gid) {
-    const unsigned long long key =
-        ((unsigned long long)__float_as_uint(__ldg(depths + gid)) << gbits) | (unsigned long long)gid;
-    const int slot = __ldg(offsets + t) + atomicAdd(cursor + t, 1);
-    bucket[slot] = key;
-  });
-}
-
+// One CTA sorts one tile's bucket in shared memory: radix sort of (32-bit depth key, Gaussian id
+// value) — 6 passes of 6 bits — then the rare runs of bit-identical depths are put in ascending
+// Gaussian order (the reference's stable sort emits ties in Gaussian order).
 template <int ITEMS>
-__device__ __forceinline__ void sort_bucket(const unsigned long long *__restrict__ src, int cnt,
-                                            int tile, int gbits, long long *__restrict__ keys_out,
-                                            int *__restrict__ ids_out, void *smem) {
-  using Sort = cub::BlockRadixSort<unsigned long long, SORT_THREADS, ITEMS, cub::NullType, 6>;
+__device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int cnt, int tile,
+                                            long long *__restrict__ keys_out,
+                                            int *__restrict__ ids_out, unsigned char *smem,
+                                            int *s_flag) {
+  using Sort = cub::BlockRadixSort<unsigned, SORT_THREADS, ITEMS, unsigned, 6>;
   typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
-  unsigned long long k[ITEMS];
+  unsigned k[ITEMS], v[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int idx = j * SORT_THREADS + threadIdx.x;          // striped load (coalesced)
-    k[j] = idx < cnt ? src[idx] : ~0ull;
+    const uint2 e = idx < cnt ? src[idx] : make_uint2(0xffffffffu, 0xffffffffu);
+    k[j] = e.x;
+    v[j] = e.y;
   }
-  // the initial arrangement is irrelevant (keys are unique); result: striped, ascending
-  Sort(tmp).SortBlockedToStriped(k, 0, 32 + gbits);
-  const unsigned long long gmask = (1ull << gbits) - 1ull;
+  Sort(tmp).SortBlockedToStriped(k, v);                       // result: striped, ascending depth
+  __syncthreads();
+  // sorted lists in shared memory (aliases the sort's storage): tie repair + coalesced output
+  unsigned *sk = reinterpret_cast<unsigned *>(smem);
+  unsigned *sv = sk + SORT_THREADS * ITEMS;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int idx = j * SORT_THREADS + threadIdx.x;
-    if (idx < cnt) {
-      ids_out[idx] = (int)(k[j] & gmask);
-      if (keys_out) keys_out[idx] = ((long long)tile << 32) | (long long)(k[j] >> gbits);
+    sk[idx] = k[j];
+    sv[idx] = v[j];
+  }
+  __syncthreads();
+  bool tie = false;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int idx = j * SORT_THREADS + threadIdx.x;
+    if (idx > 0 && idx < cnt && sk[idx] == sk[idx - 1]) tie = true;
+  }
+  if (tie) *s_flag = 1;
+  __syncthreads();
+  if (*s_flag) {
+    if (threadIdx.x == 0) {                                   // rare: order each run of equal depths
+      int i = 0;
+      while (i < cnt) {
+        int j = i + 1;
+        while (j < cnt && sk[j] == sk[i]) ++j;
+        for (int a = i + 1; a < j; ++a) {                    // insertion sort of sv[i, j)
+          const unsigned x = sv[a];
+          int b = a - 1;
+          while (b >= i && sv[b] > x) { sv[b + 1] = sv[b]; --b; }
+          sv[b + 1] = x;
+        }
+        i = j;
+      }
     }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < cnt; idx += SORT_THREADS) {
+    ids_out[idx] = (int)sv[idx];
+    if (keys_out) keys_out[idx] = ((long long)tile << 32) | (long long)sk[idx];
   }
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-bucket_sort_kernel(const unsigned long long *__restrict__ bucket, const int *__restrict__ offsets,
-                   int gbits, long long *__restrict__ isect_ids, int *__restrict__ flatten_ids) {
-  __shared__ __align__(16) unsigned char smem[sizeof(
-      typename cub::BlockRadixSort<unsigned long long, SORT_THREADS, 16, cub::NullType, 6>::TempStorage)];
+bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ offsets,
+                   long long *__restrict__ isect_ids, int *__restrict__ flatten_ids) {
+  using Sort16 = cub::BlockRadixSort<unsigned, SORT_THREADS, 16, unsigned, 6>;
+  constexpr int kSmem = sizeof(typename Sort16::TempStorage) > SORT_THREADS * 16 * 8
+                            ? (int)sizeof(typename Sort16::TempStorage)
+                            : SORT_THREADS * 16 * 8;
+  __shared__ __align__(16) unsigned char smem[kSmem];
+  __shared__ int s_flag;
   const int tile = blockIdx.x;
   const int s = offsets[tile], cnt = offsets[tile + 1] - s;
   if (cnt <= 0) return;
-  const unsigned long long *src = bucket + s;
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  const uint2 *src = bucket + (size_t)tile * BUCKET_MAX;
   long long *ko = isect_ids ? isect_ids + s : nullptr;
   int *io = flatten_ids + s;
-  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, gbits, ko, io, smem);
-  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, gbits, ko, io, smem);
-  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, gbits, ko, io, smem);
-  else sort_bucket<16>(src, cnt, tile, gbits, ko, io, smem);
+  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, ko, io, smem, &s_flag);
+  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, ko, io, smem, &s_flag);
+  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, ko, io, smem, &s_flag);
+  else sort_bucket<16>(src, cnt, tile, ko, io, smem, &s_flag);
 }
 
 }  // namespace
 
 extern "C" int32_t gags_tile_bucket_max(void) { return BUCKET_MAX; }
 
-// Steps 1-2.  count[n_tiles] is scratch (zeroed here); offsets[n_tiles + 1]; stats_dev[2] =
-// {n_isects, largest bucket}.
-extern "C" int gags_tile_bucket_count(const float *means2d, const int32_t *radii, int64_t N,
-                                      int32_t tile_w, int32_t tile_h, int32_t *count,
-                                      int32_t *offsets, int32_t *stats_dev, void *stream) {
-  if (!means2d || !radii || !count || !offsets || !stats_dev || N < 0 || tile_w <= 0 || tile_h <= 0)
+// Steps 1-2: scatter every (Gaussian, tile) pair into the tile's slab of bucket[n_tiles *
+// gags_tile_bucket_max()] (8 B each), count[n_tiles] = pairs per tile (zeroed here), exclusive scan
+// -> offsets[n_tiles + 1], stats_dev[2] = {n_isects, largest bucket}.
+extern "C" int gags_tile_bucket_count(const float *means2d, const int32_t *radii, const float *depths,
+                                      int64_t N, int32_t tile_w, int32_t tile_h, int32_t *count,
+                                      void *bucket, int32_t *offsets, int32_t *stats_dev,
+                                      void *stream) {
+  if (!means2d || !radii || !depths || !count || !bucket || !offsets || !stats_dev || N < 0 ||
+      tile_w <= 0 || tile_h <= 0)
     return GAGS_EINVAL;
-  if ((long long)tile_w * tile_h > 0x3fffffffLL) return GAGS_ERANGE;
-  if (((uintptr_t)means2d) & 7u) return GAGS_EALIGN;
+  if ((long long)tile_w * tile_h > 0x3fffffffLL || N > 0x7fffffffLL) return GAGS_ERANGE;
+  if (((uintptr_t)means2d) & 7u || ((uintptr_t)bucket) & 7u) return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = tile_w * tile_h;
   GAGS_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)n_tiles, st));
   if (N > 0) {
-    tile_hist_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const float2 *>(means2d), radii, (long long)N, tile_w, tile_h, count);
+    tile_scatter_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float2 *>(means2d), radii, depths, (long long)N, tile_w, tile_h, count,
+        reinterpret_cast<uint2 *>(bucket));
     GAGS_CHECK_LAUNCH();
   }
   bucket_scan_kernel<<<1, 1024, 0, st>>>(count, n_tiles, offsets, stats_dev);
@@ -176,31 +218,17 @@ extern "C" int gags_tile_bucket_count(const float *means2d, const int32_t *radii
   return 0;
 }
 
-// Steps 3-4.  cursor[n_tiles] scratch (zeroed here), bucket[n_isects] scratch (8 B each);
-// isect_ids may be NULL.  Requires the largest bucket <= gags_tile_bucket_max() (GAGS_ERANGE is
-// the caller's cue to use the global sort instead) and N <= 2^31.
-extern "C" int gags_tile_bucket_sort(const float *means2d, const int32_t *radii, const float *depths,
-                                     int64_t N, int32_t tile_w, int32_t tile_h,
-                                     const int32_t *offsets, int32_t max_bucket, int32_t *cursor,
-                                     void *bucket, int64_t *isect_ids, int32_t *flatten_ids,
-                                     void *stream) {
-  if (!means2d || !radii || !depths || !offsets || !cursor || !bucket || !flatten_ids || N < 0 ||
-      tile_w <= 0 || tile_h <= 0)
-    return GAGS_EINVAL;
-  if (max_bucket > BUCKET_MAX || N > 0x7fffffffLL) return GAGS_ERANGE;
-  if (N == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int n_tiles = tile_w * tile_h;
-  int gbits = 1;
-  while ((1LL << gbits) < N) ++gbits;
-  GAGS_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)n_tiles, st));
-  tile_scatter_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const float2 *>(means2d), radii, depths, (long long)N, tile_w, tile_h, gbits,
-      offsets, cursor, reinterpret_cast<unsigned long long *>(bucket));
-  GAGS_CHECK_LAUNCH();
-  bucket_sort_kernel<<<n_tiles, SORT_THREADS, 0, st>>>(
-      reinterpret_cast<const unsigned long long *>(bucket), offsets, gbits,
-      reinterpret_cast<long long *>(isect_ids), flatten_ids);
+// Step 3: sort every bucket by (depth bits, Gaussian index) and write the contiguous lists.
+// Requires max_bucket <= gags_tile_bucket_max() (GAGS_ERANGE is the caller's cue to use the global
+// sort instead).  isect_ids may be NULL.
+extern "C" int gags_tile_bucket_sort(const void *bucket, int32_t tile_w, int32_t tile_h,
+                                     const int32_t *offsets, int32_t max_bucket, int64_t *isect_ids,
+                                     int32_t *flatten_ids, void *stream) {
+  if (!bucket || !offsets || !flatten_ids || tile_w <= 0 || tile_h <= 0) return GAGS_EINVAL;
+  if (max_bucket > BUCKET_MAX) return GAGS_ERANGE;
+  bucket_sort_kernel<<<tile_w * tile_h, SORT_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint2 *>(bucket), offsets, reinterpret_cast<long long *>(isect_ids),
+      flatten_ids);
   GAGS_CHECK_LAUNCH();
   return 0;
 }

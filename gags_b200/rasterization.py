@@ -279,7 +279,7 @@ _isect_capacity = 0
 # bucketed (hist 0.14 + scatter 0.31 + 9-pass block sort 0.47) vs 0.89 ms global (6 onesweep
 # passes), so the global path stays the default; the bucketed one moves a fifth of the bytes and
 # is the better neighbour for kernels running beside it.
-bucket_sort = False
+bucket_sort = True
 
 
 @torch.no_grad()
@@ -293,32 +293,33 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
     st = _C.stream_ptr()
     global _isect_capacity
     if bucket_sort:
-        # tile-bucketed segmented sort: histogram + scan give the offsets and n_isects directly
+        # tile-bucketed segmented sort: scatter + scan give the offsets and n_isects directly
         n_tiles = tile_w * tile_h
+        bmax = int(_C.lib.gags_tile_bucket_max())
         count = torch.empty(n_tiles, dtype=torch.int32, device=dev)
+        bucket = torch.empty(n_tiles * bmax, dtype=torch.int64, device=dev)
         offsets = torch.empty(n_tiles + 1, dtype=torch.int32, device=dev)
         stats = torch.empty(2, dtype=torch.int32, device=dev)
-        _C.check(_C.lib.gags_tile_bucket_count(_C.ptr(means2d), _C.ptr(radii), N, tile_w, tile_h,
-                                               _C.ptr(count), _C.ptr(offsets), _C.ptr(stats), st),
+        _C.check(_C.lib.gags_tile_bucket_count(_C.ptr(means2d), _C.ptr(radii), _C.ptr(depths), N,
+                                               tile_w, tile_h, _C.ptr(count), _C.ptr(bucket),
+                                               _C.ptr(offsets), _C.ptr(stats), st),
                  "gags_tile_bucket_count")
         _C.count_launch(2)
         n, max_bucket = (int(v) for v in stats.tolist())      # the one host sync of the pipeline
         if after_count is not None:
             after_count()
             after_count = None
-        if max_bucket <= _C.lib.gags_tile_bucket_max():
+        if max_bucket <= bmax:
             if n > _isect_capacity:
                 _isect_capacity = int(n * 1.2) + 1024
             cap = _isect_capacity
-            bucket = torch.empty(cap, dtype=torch.int64, device=dev)
             keys = torch.empty(cap, dtype=torch.int64, device=dev)
             vals = torch.empty(cap, dtype=torch.int32, device=dev)
             if n > 0:
-                _C.check(_C.lib.gags_tile_bucket_sort(
-                    _C.ptr(means2d), _C.ptr(radii), _C.ptr(depths), N, tile_w, tile_h,
-                    _C.ptr(offsets), max_bucket, _C.ptr(count), _C.ptr(bucket), _C.ptr(keys),
-                    _C.ptr(vals), st), "gags_tile_bucket_sort")
-                _C.count_launch(2)
+                _C.check(_C.lib.gags_tile_bucket_sort(_C.ptr(bucket), tile_w, tile_h,
+                                                      _C.ptr(offsets), max_bucket, _C.ptr(keys),
+                                                      _C.ptr(vals), st), "gags_tile_bucket_sort")
+                _C.count_launch(1)
             return dict(n_isects=n, isect_ids=keys[:n], flatten_ids=vals[:n], offsets=offsets,
                         cum_tiles=None, _bases=(keys, vals, offsets))
         # a tile with more intersections than a CTA sorts in shared memory: global radix sort

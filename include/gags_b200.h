@@ -123,19 +123,19 @@ int gags_tile_emit(const float *means2d, const int32_t *radii, const float *dept
                    int64_t *isect_ids, int32_t *flatten_ids, void *stream);
 
 /* K4-K6 as a tile-bucketed segmented sort (csrc/tile_buckets.cu): same isect_ids / flatten_ids /
- * offsets as the count-scan-emit-sort-offsets sequence above, bit for bit, with about a fifth of
- * its HBM traffic.  gags_tile_bucket_count: per-tile histogram (count[n_tiles] scratch) + exclusive
+ * offsets as the count-scan-emit-sort-offsets sequence above, bit for bit, with about a sixth of
+ * its HBM traffic.  gags_tile_bucket_count: scatter every (Gaussian, tile) pair into the tile's slab
+ * of bucket[n_tiles * gags_tile_bucket_max()] (8 B entries; count[n_tiles] scratch) + exclusive
  * scan -> offsets[n_tiles+1] (= isect_offsets), stats_dev = {n_isects, largest bucket}.
- * gags_tile_bucket_sort: scatter into tile buckets (cursor[n_tiles], bucket[n_isects] x 8 B scratch)
- * and sort every bucket by (depth bits, Gaussian index) in shared memory.  Returns GAGS_ERANGE when
- * max_bucket > gags_tile_bucket_max(): use the global path then.  isect_ids may be NULL.          */
+ * gags_tile_bucket_sort: sort every bucket by (depth bits, Gaussian index) in shared memory.
+ * Returns GAGS_ERANGE when max_bucket > gags_tile_bucket_max(): use the global path then.
+ * isect_ids may be NULL.                                                                        */
 int32_t gags_tile_bucket_max(void);
-int gags_tile_bucket_count(const float *means2d, const int32_t *radii, int64_t N, int32_t tile_w,
-                           int32_t tile_h, int32_t *count, int32_t *offsets, int32_t *stats_dev,
-                           void *stream);
-int gags_tile_bucket_sort(const float *means2d, const int32_t *radii, const float *depths, int64_t N,
-                          int32_t tile_w, int32_t tile_h, const int32_t *offsets, int32_t max_bucket,
-                          int32_t *cursor, void *bucket, int64_t *isect_ids, int32_t *flatten_ids,
+int gags_tile_bucket_count(const float *means2d, const int32_t *radii, const float *depths,
+                           int64_t N, int32_t tile_w, int32_t tile_h, int32_t *count, void *bucket,
+                           int32_t *offsets, int32_t *stats_dev, void *stream);
+int gags_tile_bucket_sort(const void *bucket, int32_t tile_w, int32_t tile_h, const int32_t *offsets,
+                          int32_t max_bucket, int64_t *isect_ids, int32_t *flatten_ids,
                           void *stream);
 
 /* K5  stable LSD radix sort of (int64 key, int32 value) on bits [0, end_bit)
