@@ -187,8 +187,9 @@ def main():
 
     def opt_step():
         if world > 1:
-            parallel.allreduce_grads([pc._semantic_feature], world)
-        pc.optimizer.step()
+            parallel.allreduce_and_step(pc.optimizer, pc._semantic_feature, world)
+        else:
+            pc.optimizer.step()
         pc.optimizer.zero_grad(set_to_none=True)
 
     def step_resident(step):

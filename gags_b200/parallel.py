@@ -62,3 +62,31 @@ def sum_over_ranks(value: float, world: int, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def allreduce_and_step(optimizer, param: torch.Tensor, world: int, chunks: int = 8) -> None:
+    """Sum `param.grad` over ranks and take the (FusedAdam) optimiser step, pipelined: the gradient
+    is all-reduced in `chunks` asynchronous slices and slice i is updated as soon as its reduction
+    has landed, while slices i+1.. are still on the wire (NCCL stream).  Equivalent to
+    allreduce_grads([param]) followed by optimizer.step()."""
+    if world <= 1 or not hasattr(optimizer, "step_chunks") or param.grad is None:
+        allreduce_grads([param], world)
+        optimizer.step()
+        return
+    g = param.grad.view(-1)
+    numel = g.numel()
+    per = -(-numel // chunks)
+    per += (-per) % 4
+    works = []
+    for i in range(chunks):
+        s0, s1 = i * per, min(numel, (i + 1) * per)
+        if s0 >= s1:
+            break
+        works.append(dist.all_reduce(g[s0:s1], op=dist.ReduceOp.SUM, async_op=True))
+
+    def ready(i, n):
+        if i is None:
+            return len(works)
+        works[i].wait()            # orders the current stream behind that slice's reduction
+
+    optimizer.step_chunks(param, ready)

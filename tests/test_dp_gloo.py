@@ -31,10 +31,32 @@ def _worker(rank, world, port, out):
     mine = parallel.views_for_rank(3, rank, world, 2, 16)
     p.grad = sum(_grad_for_view(v) for v in mine)
     parallel.allreduce_grads([p], world)
+    # the pipelined variant, on a host-side optimiser exposing step_chunks (the product's FusedAdam
+    # needs a GPU): slices are reduced asynchronously and handed to the optimiser one by one
+    q = torch.nn.Parameter(torch.zeros(64, 8))
+    q.grad = sum(_grad_for_view(v) for v in mine)
+
+    class _Sgd:
+        def __init__(self):
+            self.seen = []
+
+        def step_chunks(self, prm, ready):
+            n = ready(None, None)
+            per = -(-prm.numel() // n)
+            per += (-per) % 4
+            for i in range(n):
+                ready(i, n)
+                self.seen.append(i)
+                sl = slice(i * per, min(prm.numel(), (i + 1) * per))
+                prm.data.view(-1)[sl] -= prm.grad.view(-1)[sl]
+
+    opt = _Sgd()
+    parallel.allreduce_and_step(opt, q, world, chunks=4)
     mx = parallel.max_over_ranks(float(rank + 1), world, "cpu")
     sm = parallel.sum_over_ranks(1.0, world, "cpu")
     if rank == 0:
-        torch.save({"grad": p.grad, "mine": mine, "max": mx, "sum": sm}, out)
+        torch.save({"grad": p.grad, "mine": mine, "max": mx, "sum": sm, "q": q.data,
+                    "seen": opt.seen}, out)
     dist.destroy_process_group()
 
 
@@ -56,3 +78,6 @@ def test_allreduce_equals_single_process_sum(tmp_path):
     assert res["mine"] == [12, 13]
     assert torch.allclose(res["grad"], expect, atol=1e-6)
     assert res["max"] == 2.0 and res["sum"] == 2.0
+    # pipelined all-reduce + step: every slice reduced before it was consumed
+    assert res["seen"] == [0, 1, 2, 3]
+    assert torch.allclose(res["q"], -expect, atol=1e-6)

@@ -556,6 +556,24 @@ def test_fused_adam_matches_torch_adam():
     ob.load_state_dict(oa.state_dict())                         # state layouts interchange
 
 
+def test_fused_adam_step_chunks_equals_step():
+    """the sliced step used by parallel.allreduce_and_step == one whole step."""
+    from gags_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(50000, 6, generator=g).cuda()
+    pa, pb = torch.nn.Parameter(p0.clone()), torch.nn.Parameter(p0.clone())
+    oa, ob = FusedAdam([pa], lr=1e-3, eps=1e-15), FusedAdam([pb], lr=1e-3, eps=1e-15)
+    calls = []
+    for _ in range(3):
+        gr = torch.randn(50000, 6, generator=g).cuda()
+        pa.grad, pb.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step_chunks(pb, lambda i, n: 7 if i is None else calls.append(i))
+    assert torch.equal(pa.detach(), pb.detach())
+    assert calls[:7] == list(range(7))
+    assert torch.equal(oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"])
+
+
 def test_cpu_tensors_fail_loudly():
     from gags_b200 import rasterization as R
     sc = front_scene(10, 32, 32, 3)
