@@ -111,7 +111,7 @@ template <int ITEMS>
 __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int cnt, int tile,
                                             long long *__restrict__ keys_out,
                                             int *__restrict__ ids_out, unsigned char *smem,
-                                            int *s_flag) {
+                                            unsigned *s_u) {
   using Sort = cub::BlockRadixSort<unsigned, SORT_THREADS, ITEMS, unsigned, 6>;
   typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
   unsigned k[ITEMS], v[ITEMS];
@@ -122,7 +122,25 @@ __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int c
     k[j] = e.x;
     v[j] = e.y;
   }
-  Sort(tmp).SortBlockedToStriped(k, v);                       // result: striped, ascending depth
+  // Sort key = depth bits minus the tile's smallest key: the depths of one tile span ~25 of the 32
+  // bits, i.e. 5 radix passes instead of 6.  Padding entries become range + 1 and stay last.
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    if (j * SORT_THREADS + (int)threadIdx.x < cnt) { kmin = min(kmin, k[j]); kmax = max(kmax, k[j]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_u[1], kmin); atomicMax(&s_u[2], kmax); }
+  __syncthreads();
+  kmin = s_u[1];
+  const unsigned pad = s_u[2] - kmin + 1u;                    // > every real key; no overflow: the
+#pragma unroll                                                // keys are finite positive floats
+  for (int j = 0; j < ITEMS; ++j)
+    k[j] = (j * SORT_THREADS + (int)threadIdx.x < cnt) ? k[j] - kmin : pad;
+  Sort(tmp).SortBlockedToStriped(k, v, 0, 32 - __clz(pad));    // result: striped, ascending depth
   __syncthreads();
   // sorted lists in shared memory (aliases the sort's storage): tie repair + coalesced output
   unsigned *sk = reinterpret_cast<unsigned *>(smem);
@@ -130,7 +148,7 @@ __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int c
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int idx = j * SORT_THREADS + threadIdx.x;
-    sk[idx] = k[j];
+    sk[idx] = k[j] + kmin;
     sv[idx] = v[j];
   }
   __syncthreads();
@@ -140,9 +158,9 @@ __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int c
     const int idx = j * SORT_THREADS + threadIdx.x;
     if (idx > 0 && idx < cnt && sk[idx] == sk[idx - 1]) tie = true;
   }
-  if (tie) *s_flag = 1;
+  if (tie) s_u[0] = 1u;
   __syncthreads();
-  if (*s_flag) {
+  if (s_u[0]) {
     if (threadIdx.x == 0) {                                   // rare: order each run of equal depths
       int i = 0;
       while (i < cnt) {
@@ -173,19 +191,21 @@ bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ off
                             ? (int)sizeof(typename Sort16::TempStorage)
                             : SORT_THREADS * 16 * 8;
   __shared__ __align__(16) unsigned char smem[kSmem];
-  __shared__ int s_flag;
+  __shared__ unsigned s_u[3];                     // tie flag, smallest key, largest key
   const int tile = blockIdx.x;
   const int s = offsets[tile], cnt = offsets[tile + 1] - s;
   if (cnt <= 0) return;
-  if (threadIdx.x == 0) s_flag = 0;
+  if (threadIdx.x == 0) { s_u[0] = 0u; s_u[1] = 0xffffffffu; s_u[2] = 0u; }
   __syncthreads();
   const uint2 *src = bucket + (size_t)tile * BUCKET_MAX;
   long long *ko = isect_ids ? isect_ids + s : nullptr;
   int *io = flatten_ids + s;
-  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, ko, io, smem, &s_flag);
-  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, ko, io, smem, &s_flag);
-  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, ko, io, smem, &s_flag);
-  else sort_bucket<16>(src, cnt, tile, ko, io, smem, &s_flag);
+  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, ko, io, smem, s_u);
+  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, ko, io, smem, s_u);
+  else if (cnt <= SORT_THREADS * 5) sort_bucket<5>(src, cnt, tile, ko, io, smem, s_u);
+  else if (cnt <= SORT_THREADS * 6) sort_bucket<6>(src, cnt, tile, ko, io, smem, s_u);
+  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, ko, io, smem, s_u);
+  else sort_bucket<16>(src, cnt, tile, ko, io, smem, s_u);
 }
 
 }  // namespace
