@@ -53,8 +53,9 @@ constexpr int RING = TC_RING;
 constexpr int TC_THREADS = 448;   // 13 role warps + the weight-tile store warp
 
 struct TcCtl {
-  uint64_t list[2], full[2], free_[2];
+  uint64_t list[2], full[2], free_[2], sdone[2], afull[2];
   uint32_t tmem_base;
+  int term;
   int gcount[2];
   int skip[2];
   int done_warps, skip_from, any_mma;
@@ -121,10 +122,12 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     for (int k = 0; k < 2; ++k) {
       mbar_init(&ctl.list[k], 4);                  // scanner warps
       mbar_init(&ctl.full[k], 8);                  // pixel + converter warps
-      mbar_init(&ctl.free_[k], cache ? 2 : 1);     // MMA commit (+ the tile store has read the stage)
+      mbar_init(&ctl.free_[k], 1);                 // MMA commit: stage's B tile and records reusable
+      mbar_init(&ctl.sdone[k], 1);                 // training: the tile store has read the A stage
+      mbar_init(&ctl.afull[k], 4);                 // training: pixel warps -> store warp, A tile written
       ctl.gcount[k] = 0; ctl.skip[k] = 0;
     }
-    ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0;
+    ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0; ctl.term = -1;
     mbar_fence_init();
   }
   if (tid < 256) ctl.bgs[tid] = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
@@ -151,9 +154,26 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
       if (warp == 0) TC_STAMP(0, i, 1);
       const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
-      if (nb == 0) break;
+      // (training) the weight tile of batch i-2 must have left this stage before it is overwritten;
+      // only the writers of the A tile wait for that, not the scanner / converters
+      const bool wait_store = cache && i >= 2;
+      if (nb == 0) {
+        // tell the store warp that batch i does not exist.  Its barrier (afull) is only ever
+        // advanced by the pixel warps, and only after the store of batch i-2 has been seen
+        // (sdone), so the store warp can never be two phases behind it.
+        if (cache) {
+          if (wait_store) mbar_wait_bounded(&ctl.sdone[st], ((i >> 1) - 1) & 1);
+          if (warp == 0 && lane == 0) {
+            *reinterpret_cast<volatile int *>(&ctl.term) = i;
+            __threadfence_block();
+          }
+          mbar_arrive_warp(&ctl.afull[st]);
+        }
+        break;
+      }
       unsigned char *arow = sA + st * 16384;
       const bool wdone = __all_sync(0xffffffffu, tc_pixel_done(ps));
+      if (wait_store) mbar_wait_bounded(&ctl.sdone[st], ((i >> 1) - 1) & 1);
       if (wdone) {
         if (lane == 0) atomicAdd(&ctl.skip[st], 1);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -171,6 +191,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (warp == 0) TC_STAMP(0, i, 2);
       fence_async_smem();
       mbar_arrive_warp(&ctl.full[st]);
+      if (cache) mbar_arrive_warp(&ctl.afull[st]);
       if (warp == 0) TC_STAMP(0, i, 3);
       if (!counted && __all_sync(0xffffffffu, tc_pixel_done(ps))) {
         counted = true;
@@ -293,9 +314,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         load_row(i, nb, skipb, row + 4, v[j]);
       }
       if (warp == 8) TC_STAMP(1, i, 3);
-      int nb2;
-      bool skip2;
-      header(i + 1, nb2, skip2);
+      // the next batch's first rows are prefetched only if its list is already out: never block
+      // on it here (its publication may itself be waiting for this batch to be consumed)
+      int nb2 = -1;
+      bool skip2 = false;
+      const bool ahead = __all_sync(0xffffffffu,
+                                    mbar_test_wait(&ctl.list[(i + 1) & 1], ((i + 1) >> 1) & 1));
+      if (ahead) header(i + 1, nb2, skip2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int row = cw * 8 + 4 + j;
@@ -305,6 +330,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       fence_async_smem();
       mbar_arrive_warp(&ctl.full[st]);
       if (warp == 8) TC_STAMP(1, i, 4);
+      if (!ahead) {
+        header(i + 1, nb2, skip2);
+        if (nb2 > 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
+        }
+      }
       nb = nb2;
       skipb = skip2;
     }
@@ -358,10 +390,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       int stored = 0;
       for (int i = 0;; ++i) {
         const int st = i & 1;
-        mbar_wait_bounded(&ctl.list[st], (i >> 1) & 1);
-        const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
-        if (nb == 0) break;
-        mbar_wait_bounded(&ctl.full[st], (i >> 1) & 1);
+        mbar_wait_bounded(&ctl.afull[st], (i >> 1) & 1);
+        if (*reinterpret_cast<volatile int *>(&ctl.term) == i) break;
         const int votes_now = *reinterpret_cast<volatile int *>(&ctl.skip[st]);
         const int votes = votes_now - seen[st];
         seen[st] = votes_now;
@@ -374,7 +404,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        mbar_arrive(&ctl.free_[st]);
+        mbar_arrive(&ctl.sdone[st]);
       }
       wcount[blockIdx.y * gridDim.x + blockIdx.x] = stored;
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -166,7 +166,7 @@ __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Scanner: per-thread state of the 128-thread warp group that walks a tile's depth-sorted list 128
+// Scanner: per-thread state of the NT-thread warp group that walks a tile's depth-sorted list NT
 // entries at a time, culls every Gaussian whose alpha >= 1/255 bounding box misses the half tile
 // (exact: such a Gaussian contributes to no pixel of it) and appends the survivors, in list order,
 // to a ring in shared memory.  One round = ids load (prefetched a round ahead) -> geometry gather
@@ -174,7 +174,8 @@ __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
 // `finish` consumes them, so a caller can put other work between the two.
 // Uses named barrier 1 (128 threads).
 // ------------------------------------------------------------------------------------------------
-struct TcScanner {
+template <int NT>
+struct TcScannerT {
   const float4 *geom;
   const int *ids;
   float4 *rg0, *rg1;
@@ -206,7 +207,7 @@ struct TcScanner {
       pa0 = __ldg(geom + pend_gid * 2);
       pa1 = __ldg(geom + pend_gid * 2 + 1);
     }
-    scan += 128;
+    scan += NT;
     nxt_gid = (scan + p < e) ? __ldg(ids + scan + p) : -1;
     pending = true;
   }
@@ -215,10 +216,10 @@ struct TcScanner {
     const bool keep = mask != 0u;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) wcnt[pw] = __popc(bal);
-    named_bar_sync(1, 128);
+    named_bar_sync(1, NT);
     int basec = qtail, total = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NT / 32; ++k) {
       const int c = wcnt[k];
       if (k < pw) basec += c;
       total += c;
@@ -231,6 +232,7 @@ struct TcScanner {
     }
     qtail += total;
     pending = false;
-    named_bar_sync(1, 128);
+    named_bar_sync(1, NT);
   }
 };
+using TcScanner = TcScannerT<128>;

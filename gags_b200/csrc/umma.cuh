@@ -5,6 +5,7 @@
 // stride between 8-row groups, store swizzle) were verified on a B200 with tools/umma_probe.cu.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdio>
 #include "common.cuh"
 
 // ---- mbarrier helpers with a bounded spin (a protocol bug traps instead of hanging the GPU) ----
@@ -21,10 +22,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
 #pragma unroll 1
   for (int i = 0; i < (1 << 20); ++i)
     if (mbar_try_wait(bar, parity)) return;
+#ifdef GAGS_TC_TIMING
+  printf("mbar timeout: block (%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, smem_u32(bar), parity);
+#endif
   __trap();
 }
 
