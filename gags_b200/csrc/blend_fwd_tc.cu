@@ -55,7 +55,7 @@ constexpr int TC_THREADS = 448;   // 13 role warps + the weight-tile store warp
 struct TcCtl {
   uint64_t list[2], full[2], free_[2], sdone[2], afull[2];
   uint32_t tmem_base;
-  int term;
+  int term, bg_nonzero[8];
   int gcount[2];
   int skip[2];
   int done_warps, skip_from, any_mma;
@@ -130,7 +130,14 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0; ctl.term = -1;
     mbar_fence_init();
   }
-  if (tid < 256) ctl.bgs[tid] = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
+  // background: staged once; an all-zero background (the reference's default, black) is detected
+  // here so that the epilogue skips its T * bg term and the shared-memory reads behind it
+  if (tid < 256) {
+    const float b = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
+    ctl.bgs[tid] = b;
+    const bool nzw = __any_sync(0xffffffffu, b != 0.f);
+    if (lane == 0) ctl.bg_nonzero[warp] = nzw ? 1 : 0;
+  }
   if (warp == 12) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
   tc_fence_before();
   __syncthreads();
@@ -420,6 +427,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   if (warp == 0) TC_STAMP(3, 0, 2);
   if (warp < 12) {
     const bool any = ctl.any_mma != 0;
+    bool use_bg = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) use_bg = use_bg || (ctl.bg_nonzero[k] != 0);
     const int q = warp & 3, third = warp >> 2;
     float *stg = reinterpret_cast<float *>(sm + warp * 4096);
     const int nchunk = (nch + 31) >> 5;
@@ -437,7 +447,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       for (int cc = 0; cc < 8; ++cc) {
         float4 v = make_float4(__uint_as_float(r[cc * 4]), __uint_as_float(r[cc * 4 + 1]),
                                __uint_as_float(r[cc * 4 + 2]), __uint_as_float(r[cc * 4 + 3]));
-        if (bg != nullptr) {
+        if (use_bg) {
           const float4 b = *reinterpret_cast<const float4 *>(&ctl.bgs[c0 + cc * 4]);
           v.x = fmaf(Tp, b.x, v.x); v.y = fmaf(Tp, b.y, v.y);
           v.z = fmaf(Tp, b.z, v.z); v.w = fmaf(Tp, b.w, v.w);
