@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="override N (debug only; invalidates value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="separate L1 kernel + autograd backward instead of l1_backward_fused")
     return ap.parse_args()
 
 
@@ -136,7 +138,7 @@ def main():
     from gags_b200.gaussian_renderer import render
     from gags_b200.scene import GaussianModel
     from gags_b200.synthetic import CONFIGS, config_scene
-    from gags_b200.utils.loss_utils import l1_loss_segmap_fused
+    from gags_b200.utils.loss_utils import l1_backward_fused, l1_loss_segmap_fused
 
     rank, world, local = parallel.init_from_env("nccl")
     if world != args.gpus and world > 1:
@@ -181,9 +183,12 @@ def main():
 
     def one_view(cam, target):
         pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
-        loss = l1_loss_segmap_fused(pkg["render"], target[0], target[1])
-        loss.backward()
-        return loss
+        if args.unfused_loss:
+            loss = l1_loss_segmap_fused(pkg["render"], target[0], target[1])
+            loss.backward()
+            return loss
+        # loss + loss.backward() as one call: the L1 gradient is formed inside the feature backward
+        return l1_backward_fused(pkg["render"], target[0], target[1])
 
     def opt_step():
         if world > 1:
@@ -224,15 +229,23 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         l0 = _C.launches()
+        a0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        marks = []
         e0.record()
         last = None
         for i in range(steps):
             last = fn(warmup + i)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         barrier()
         sampler.stop_flag = True
         sampler.join()
         ms = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
+        # diagnostics only: the slowest single step and the cudaMallocs that landed in the region
+        per = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        timed.diag = {"max_step_ms": round(max(per), 3), "min_step_ms": round(min(per), 3),
+                      "device_allocs": torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - a0}
         return ms, last, sampler.summary(), _C.launches() - l0
 
     # Untimed priming (like the reference's scene loading): the grow-only workspaces (intersection
@@ -243,6 +256,7 @@ def main():
         step_resident(10_000 + i)
     ms, _, clocks, launches = timed(step_resident, args.steps, args.warmup)
     alloc_stats = {"reserved_GB": round(torch.cuda.max_memory_reserved(dev) / 1e9, 2)}
+    alloc_stats.update(timed.diag)
     views_total = args.steps * kviews * world
     value = views_total / (ms * 1e-3)
 
@@ -270,9 +284,12 @@ def main():
             cam = cams[(7 * i) % n_views]
             pkg = render(cam, pc, None, bg)
             R._mark("loss_start")
-            loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
-            R._mark("loss")
-            loss.backward()
+            if args.unfused_loss:
+                loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
+                R._mark("loss")
+                loss.backward()
+            else:
+                loss = l1_backward_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
             R._mark("backward_end")
             pc.optimizer.step()
             R._mark("adam")

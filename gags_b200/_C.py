@@ -65,6 +65,8 @@ SIGNATURES = {
     "gags_blend_fwd_cached": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                         _p, _p]),
     "gags_blend_bwd_features_cached": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gags_blend_bwd_features_cached_l1": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                                                    _p, _i32, _f, _p, _p, _p]),
     "gags_blend_bwd_full": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                       _p, _p, _p]),
     "gags_l1_loss_fused": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p]),

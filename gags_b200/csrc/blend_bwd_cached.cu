@@ -97,12 +97,27 @@ __device__ __forceinline__ CbJob cb_job(long long j, int nblk, int tile_w, int c
   return jb;
 }
 
+// Fused L1 loss (L1 = true): `v_render` is then the RENDER itself and the staging warps turn it into
+// the loss gradient on the fly, scale * m * sign(render - emb[seg]), while summing m * |render -
+// emb[seg]| into *loss — the semantics of l1_loss_segmap_kernel (train_ops.cu), without the 2 GB
+// gradient map ever existing in HBM.  Every (pixel, channel) is staged by exactly one job, half
+// tiles without Gaussians included (they only contribute to the loss).
+struct CbL1 {
+  const int *seg;
+  const float *emb;
+  const float *mask;
+  float *loss;
+  int n_seg;
+  float scale;
+};
+
+template <bool L1>
 __global__ void __launch_bounds__(CB_THREADS, 2)
 blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, long long njobs,
                  const int *__restrict__ offsets, const unsigned char *__restrict__ wcache,
                  const int *__restrict__ wmeta, const int *__restrict__ wlist,
                  const int *__restrict__ wcount, int *__restrict__ jobctr,
-                 const float *__restrict__ v_render, float *__restrict__ v_colors) {
+                 const float *__restrict__ v_render, float *__restrict__ v_colors, CbL1 l1) {
   using L = CbLayout;
   // The kernel has no static shared memory, so the dynamic window starts at the CTA's shared-memory
   // base (1 KB aligned, which SWIZZLE_128B needs); the layout uses every byte of the two-CTAs-per-SM
@@ -150,6 +165,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
     const uint32_t coff = (uint32_t)((n0 >> 6) & 1) * 16384u + (uint32_t)((n0 & 63) >> 3) * 16u;
     unsigned char *vhi = sV, *vlo = sV + L::VPART;
     int jn = 0;                                     // non-empty jobs staged so far
+    float l1acc = 0.f;
     for (int k = 0;; ++k) {
       // fetch + publish the k-th job id (staging leads every other role)
       if (tid == 0) {
@@ -162,28 +178,86 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
       const long long j = (long long)*reinterpret_cast<volatile int *>(&ctl.jobq[k & (CB_JQ - 1)]);
       if (j < 0) break;
       const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
-      if (jb.nbat <= 0) continue;
+      const bool live = jb.nbat > 0;
+      if (!L1 && !live) continue;
       const bool chan_ok = n0 < jb.cvalid;
       const float *vbase = v_render + jb.cfirst + n0;
+      // pixels per round: the fused-loss form also holds the target rows, so it takes half as many
+      constexpr int PJ = L1 ? 4 : 8;
       // first half of the loads may fly before the previous job's MMAs have released the buffer
 #pragma unroll 1
-      for (int round = 0; round < 2; ++round) {
-        float4 v[8][2];
+      for (int round = 0; round < 16 / PJ; ++round) {
+        float4 v[PJ][2];
+        if constexpr (L1) {
+          // segment id (and mask) first: the target row's address depends on it
+          int sg[PJ];
+          float mk[PJ];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int ql = 2 * (round * 8 + jj) + (lane >> 4);   // pixel inside this 8x4 block
-          const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
-          v[jj][0] = v[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (chan_ok && xx < W && yy < H) {
-            const float4 *src = reinterpret_cast<const float4 *>(vbase + ((size_t)yy * W + xx) * D);
-            v[jj][0] = ldg_nc4(src);
-            v[jj][1] = ldg_nc4(src + 1);
+          for (int jj = 0; jj < PJ; ++jj) {
+            const int ql = 2 * (round * PJ + jj) + (lane >> 4);
+            const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+            sg[jj] = -1;
+            mk[jj] = 1.f;
+            if (chan_ok && xx < W && yy < H) {
+              sg[jj] = __ldg(l1.seg + (size_t)yy * W + xx);
+              if (l1.mask) mk[jj] = fabsf(__ldg(l1.mask + (size_t)yy * W + xx));
+            } else {
+              mk[jj] = 0.f;
+            }
+          }
+          float4 t[PJ][2];
+#pragma unroll
+          for (int jj = 0; jj < PJ; ++jj) {
+            const int ql = 2 * (round * PJ + jj) + (lane >> 4);
+            const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+            v[jj][0] = v[jj][1] = t[jj][0] = t[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chan_ok && xx < W && yy < H) {
+              const float4 *src = reinterpret_cast<const float4 *>(vbase + ((size_t)yy * W + xx) * D);
+              v[jj][0] = ldg_nc4(src);
+              v[jj][1] = ldg_nc4(src + 1);
+              if (sg[jj] >= 0 && sg[jj] < l1.n_seg) {
+                const float4 *te =
+                    reinterpret_cast<const float4 *>(l1.emb + (size_t)sg[jj] * D + jb.cfirst + n0);
+                t[jj][0] = __ldg(te);
+                t[jj][1] = __ldg(te + 1);
+              } else {
+                mk[jj] = 0.f;                          // no target for this pixel: weight 0
+              }
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < PJ; ++jj) {
+            const float sc = l1.scale * mk[jj];
+            float part = 0.f;
+#define GAGS_L1C(h, c)                                              \
+            {                                                       \
+              const float d = v[jj][h].c - t[jj][h].c;              \
+              part += fabsf(d);                                     \
+              v[jj][h].c = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);    \
+            }
+            GAGS_L1C(0, x) GAGS_L1C(0, y) GAGS_L1C(0, z) GAGS_L1C(0, w)
+            GAGS_L1C(1, x) GAGS_L1C(1, y) GAGS_L1C(1, z) GAGS_L1C(1, w)
+#undef GAGS_L1C
+            l1acc = fmaf(mk[jj], part, l1acc);
+          }
+          if (!live) continue;                         // empty half tile: loss only
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < PJ; ++jj) {
+            const int ql = 2 * (round * PJ + jj) + (lane >> 4);   // pixel inside this 8x4 block
+            const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+            v[jj][0] = v[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chan_ok && xx < W && yy < H) {
+              const float4 *src = reinterpret_cast<const float4 *>(vbase + ((size_t)yy * W + xx) * D);
+              v[jj][0] = ldg_nc4(src);
+              v[jj][1] = ldg_nc4(src + 1);
+            }
           }
         }
         if (round == 0 && jn > 0) mbar_wait_bounded(&ctl.vfree, (uint32_t)((jn - 1) & 1));
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int r = q * 32 + 2 * (round * 8 + jj) + (lane >> 4);   // row of the K = 128 px dim
+        for (int jj = 0; jj < PJ; ++jj) {
+          const int r = q * 32 + 2 * (round * PJ + jj) + (lane >> 4);   // row of the K = 128 px dim
           uint4 h, l;
           split_pack2(v[jj][0].x, v[jj][0].y, h.x, l.x);
           split_pack2(v[jj][0].z, v[jj][0].w, h.y, l.y);
@@ -195,10 +269,16 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
           *reinterpret_cast<uint4 *>(vlo + off) = l;
         }
       }
+      if (!live) continue;
       fence_async_smem();
       mbar_arrive_warp(&ctl.vfull);
       if (warp == 0 && jn < 2) CB_STAMP(3, 0, 1 + jn);
       ++jn;
+    }
+    if constexpr (L1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l1acc += __shfl_xor_sync(0xffffffffu, l1acc, o);
+      if (lane == 0) atomicAdd(l1.loss, l1acc);
     }
   } else if (warp < 8) {
     // ======================= epilogue ==============================================================
@@ -323,17 +403,18 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
   if (warp == 9) tmem_dealloc<L::TCOLS>(tb);
 }
 
+template <bool L1>
 int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const unsigned char *wcache,
               const int *wmeta, const int *wlist, int *wcount, const float *v_render,
-              float *v_colors, cudaStream_t st) {
+              float *v_colors, CbL1 l1, cudaStream_t st) {
   using L = CbLayout;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
   const int nblk = (nch + 127) / 128;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<L1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -344,9 +425,9 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
   cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
-  blend_bwd_cached<<<grid, CB_THREADS, L::BYTES, st>>>(
+  blend_bwd_cached<L1><<<grid, CB_THREADS, L::BYTES, st>>>(
       D, ch0, nch, nblk, W, H, tw, njobs, offsets, wcache, wmeta, wlist, wcount, jobctr, v_render,
-      v_colors);
+      v_colors, l1);
   return (int)cudaGetLastError();
 }
 
@@ -365,8 +446,37 @@ extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t 
   const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = launch_cb(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount, v_render,
-                             v_colors, st);
+    const int rc = launch_cb<false>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
+                                    v_render, v_colors, CbL1{}, st);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// Fused L1 loss + feature backward (see CbL1): *loss_out += sum m |render - emb[seg]|; the caller
+// zeroes it and scales by 1 / (H W D).  grad_scale is d loss / d render's magnitude (1 / (H W D)
+// for the mean).  Replaces gags_l1_loss_segmap + gags_blend_bwd_features_cached.
+extern "C" int gags_blend_bwd_features_cached_l1(int32_t D, int32_t width, int32_t height,
+                                                 const int32_t *offsets, const void *wcache,
+                                                 const int32_t *wmeta, const int32_t *wlist,
+                                                 int32_t *wcount, const float *render,
+                                                 const int32_t *seg, const float *emb,
+                                                 const float *mask, int32_t n_seg, float grad_scale,
+                                                 float *loss_out, float *v_colors, void *stream) {
+  if (!offsets || !wcache || !wmeta || !wlist || !wcount || !render || !v_colors || !seg || !emb ||
+      !loss_out)
+    return GAGS_EINVAL;
+  if (D <= 32 || D % 16 != 0 || width <= 0 || height <= 0 || n_seg < 1) return GAGS_EINVAL;
+  if (!gags_aligned16(wcache) || !gags_aligned16(render) || !gags_aligned16(v_colors) ||
+      !gags_aligned16(emb))
+    return GAGS_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
+  const CbL1 l1{seg, emb, mask, loss_out, n_seg, grad_scale};
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const int rc = launch_cb<true>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
+                                   render, v_colors, l1, st);
     if (rc != 0) return rc;
   }
   return 0;

@@ -76,7 +76,8 @@ struct TcLayout {
   static constexpr int STG_END = 12 * 4096;            // epilogue staging: 12 warps x 4 KB from 0
   static constexpr int CTL_OFF = (RING_OFF + RING * 36) > STG_END ? (RING_OFF + RING * 36) : STG_END;
   static constexpr int BYTES = CTL_OFF + (int)sizeof(TcCtl) + 1024;   // + alignment slack
-  static constexpr int TCOLS = NATOM == 1 ? 64 : (NATOM == 2 ? 128 : 256);
+  static constexpr int MB = (NATOM + 1) / 2;           // 128-channel blocks (MMA M)
+  static constexpr int TCOLS = MB * 128;               // accumulator: lane = channel, column = pixel
 };
 // two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
 static_assert(TcLayout<4>::BYTES <= (233472 / 2 - 1024), "forward TC kernel must fit twice per SM");
@@ -350,9 +351,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   } else if (warp == 12) {
     // ======================= MMA issuer ============================================================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(nch, false, true);
-      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB), 4096, 1024);
+      // transposed product: D[channel, pixel] += F^T[channel, g] * W^T[g, pixel].  The feature tile
+      // is the MN-major A operand (one 128-channel block per instruction), the weight tile the
+      // K-major B operand (N = 128 pixels), so that a TMEM lane is a channel and the epilogue's
+      // warp-wide stores are contiguous in the channel-last output without a transpose.
+      const uint32_t idesc = umma_idesc_bf16(128, true, false);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t f_desc0 = umma_desc_sw128(smem_u32(sB), 4096, 1024);
       uint32_t acc = 0;
       int seen[2] = {0, 0};
       for (int i = 0;; ++i) {
@@ -371,14 +376,19 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           const int nk = (nb + 15) >> 4;
           for (int ks = 0; ks < nk; ++ks) {
             // only the 14-bit start-address field (16-B units) changes between descriptors
-            const uint64_t ahi = a_desc0 + (uint64_t)((st * 16384 + ks * 32) >> 4);
-            const uint64_t alo = ahi + (uint64_t)(64 >> 4);
-            const uint64_t bhi = b_desc0 + (uint64_t)(((st * 2) * L::BPART + ks * 2048) >> 4);
-            const uint64_t blo = bhi + (uint64_t)(L::BPART >> 4);
-            umma_bf16_ss(tb, ahi, bhi, idesc, acc);
+            const uint64_t whi = w_desc0 + (uint64_t)((st * 16384 + ks * 32) >> 4);
+            const uint64_t wlo = whi + (uint64_t)(64 >> 4);
+#pragma unroll
+            for (int mb = 0; mb < L::MB; ++mb) {
+              const uint64_t fhi =
+                  f_desc0 + (uint64_t)(((st * 2) * L::BPART + mb * 8192 + ks * 2048) >> 4);
+              const uint64_t flo = fhi + (uint64_t)(L::BPART >> 4);
+              const uint32_t d = tb + (uint32_t)(mb * 128);
+              umma_bf16_ss(d, fhi, whi, idesc, acc);
+              umma_bf16_ss(d, flo, whi, idesc, 1);
+              umma_bf16_ss(d, fhi, wlo, idesc, 1);
+            }
             acc = 1;
-            umma_bf16_ss(tb, ahi, blo, idesc, 1);
-            umma_bf16_ss(tb, alo, bhi, idesc, 1);
           }
         }
         umma_commit(&ctl.free_[st]);
@@ -431,40 +441,46 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) use_bg = use_bg || (ctl.bg_nonzero[k] != 0);
     const int q = warp & 3, third = warp >> 2;
-    float *stg = reinterpret_cast<float *>(sm + warp * 4096);
-    const int nchunk = (nch + 31) >> 5;
-    const float Tp = ctl.Tfin[q * 32 + lane];
-    for (int cidx = third; cidx < nchunk; cidx += 3) {
-      const int c0 = cidx * 32;
+    // one item = one 128-channel block x this warp's 32 channels x 32 pixels (a 8 x 4 block)
+    for (int idx = third; idx < L::MB * 4; idx += 3) {
+      const int mb = idx >> 2, pc = idx & 3;
+      const int ch = mb * 128 + q * 32 + lane;
+      if (mb * 128 + q * 32 >= nch) continue;                      // warp-uniform
       uint32_t r[32];
       if (any) {
-        tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128 + pc * 32), r);
       } else {
 #pragma unroll
         for (int k = 0; k < 32; ++k) r[k] = 0u;
       }
+      if (use_bg) {
+        const float b = ch < nch ? ctl.bgs[ch] : 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        float4 v = make_float4(__uint_as_float(r[cc * 4]), __uint_as_float(r[cc * 4 + 1]),
-                               __uint_as_float(r[cc * 4 + 2]), __uint_as_float(r[cc * 4 + 3]));
-        if (use_bg) {
-          const float4 b = *reinterpret_cast<const float4 *>(&ctl.bgs[c0 + cc * 4]);
-          v.x = fmaf(Tp, b.x, v.x); v.y = fmaf(Tp, b.y, v.y);
-          v.z = fmaf(Tp, b.z, v.z); v.w = fmaf(Tp, b.w, v.w);
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(fmaf(ctl.Tfin[pc * 32 + j], b, __uint_as_float(r[j])));
+      }
+      if (ch >= nch) continue;
+      const int xb = x0 + ((pc & 1) << 3), yb = y0 + ((pc >> 1) << 2);
+      float *dst = render + ((size_t)yb * W + xb) * D + ch0 + ch;
+      const size_t rowstride = (size_t)W * D;
+      if (xb + 8 <= W && yb + 4 <= H) {                            // interior block: no predicates
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+#pragma unroll
+          for (int x = 0; x < 8; ++x) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[y * 8 + x]));
+          dst += rowstride;
         }
-        *reinterpret_cast<float4 *>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) = v;
-      }
-      __syncwarp();
+      } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int ql = it * 4 + (lane >> 3), cc = lane & 7;
-        const float4 v = *reinterpret_cast<const float4 *>(stg + ql * 32 + ((cc ^ (ql & 7)) << 2));
-        const int xx = x0 + ((q & 1) << 3) + (ql & 7), yy = y0 + ((q >> 1) << 2) + (ql >> 3);
-        const int ch = c0 + cc * 4;
-        if (xx < W && yy < H && ch < nch)
-          stg_cs4(reinterpret_cast<float4 *>(render + ((size_t)yy * W + xx) * D + ch0 + ch), v);
+        for (int y = 0; y < 4; ++y) {
+          if (yb + y < H) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if (xb + x < W) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[y * 8 + x]));
+          }
+          dst += rowstride;
+        }
       }
-      __syncwarp();
     }
   }
   if (warp == 0) TC_STAMP(3, 0, 3);

@@ -145,6 +145,9 @@ __device__ __forceinline__ void stg_cs4(float4 *p, float4 v) {
                "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void stg_cs1(float *p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void red_add4(float *p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)

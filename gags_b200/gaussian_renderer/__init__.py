@@ -64,6 +64,9 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, feature_mode=True
         scaling_modifier=smod, flags=flags)
 
     rendered_image = render_colors.permute(2, 0, 1)            # [H,W,D] -> [D,H,W] (a view)
+    fused = getattr(render_colors, "_gags_fused", None)        # see rasterization.fused_l1_backward
+    if fused is not None:
+        rendered_image._gags_fused = fused
     radii = info["radii"]
     try:
         info["means2d"].retain_grad()

@@ -93,7 +93,22 @@ def _mark(name: str) -> None:
 #     lookahead (and the host run-ahead, through the n_isects readback) to one view;
 #   * every buffer produced on the side stream is record_stream()ed on the consuming stream.
 import os as _os
-lookahead = _os.environ.get("GAGS_B200_LOOKAHEAD", "1") != "0"
+# Off by default since the loss moved into the backward (fused_l1_backward): without the HBM-bound
+# loss pass to hide behind, the stage only ever overlaps the L2-reduction-bound backward and Adam,
+# and both lose more than the stage gains (measured: 6.06 ms/step off, 6.57 ms/step on).
+lookahead = _os.environ.get("GAGS_B200_LOOKAHEAD", "0") != "0"
+# Zero the backward's [N, D] accumulation buffer on a second stream, launched right AFTER the
+# forward blend kernel: the forward is issue / shared-memory bound and leaves thread slots and HBM
+# bandwidth free, so the fill's CTAs run in its shadow instead of in front of the backward.
+prezero_overlap = _os.environ.get("GAGS_B200_PREZERO", "1") != "0"
+_zero_streams: Dict = {}
+
+
+def _zero_stream(dev):
+    s = _zero_streams.get(dev.index)
+    if s is None:
+        s = _zero_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
 _side: Dict = {}
 
 
@@ -368,6 +383,94 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
 # ------------------------------------------------------------------------------------------------
 # K7 / K8
 # ------------------------------------------------------------------------------------------------
+def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
+    """The [N, D] buffer the feature backward accumulates into, and the leaf it belongs to when the
+    reduction goes straight into `.grad` (direct_grad_accumulation)."""
+    sink = ctx.sink if (need_col and not need_geo) else None
+    if sink is not None and sink.grad is not None and sink.grad.is_contiguous() \
+            and sink.grad.dtype == torch.float32:
+        v_colors = sink.grad                     # accumulate in place: nothing to zero or add
+        ctx.prezero = None
+    elif need_col and ctx.prezero is not None:
+        v_colors, evz, _ = ctx.prezero
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(evz)
+        v_colors.record_stream(cur)
+        ctx.prezero = None
+    else:
+        v_colors = torch.zeros(N, D, device=dev) if need_col else None
+    return v_colors, sink
+
+
+class _FusedHandle:
+    """What fused_l1_backward needs from one cached forward (attached to the render tensor)."""
+    __slots__ = ("ctx", "cols", "offsets", "render_ptr")
+
+    def __init__(self, ctx, cols, offsets, render_ptr):
+        self.ctx, self.cols, self.offsets, self.render_ptr = ctx, cols, offsets, render_ptr
+
+
+_last_cached_ctx = None
+
+
+def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
+    """loss = mean(|render - emb[seg]| * mask) AND its backward into the feature table in one
+    kernel: equivalent to `loss = l1_loss_segmap_fused(render, seg, emb, mask); loss.backward()`
+    (train.py:162-165 with the compact target), but the loss gradient is formed inside the cached
+    feature backward's staging warps, so the [H,W,D] gradient map (2 GB at config 3) is neither
+    written nor read.  `render_dhw` must be the tensor render() / rasterize_view() returned for a
+    forward that kept its weight tiles (frozen geometry, trainable features); anything else falls
+    back to the two-kernel form.  Returns the detached loss."""
+    from .utils.loss_utils import l1_loss_segmap_fused
+    h = getattr(render_dhw, "_gags_fused", None)
+    r = render_dhw.permute(1, 2, 0) if render_dhw.dim() == 3 else None
+    ok = (h is not None and h.ctx.lease is not None and r is not None and r.is_contiguous()
+          and r.data_ptr() == h.render_ptr and seg_hw.dtype == torch.int32
+          and emb.dtype == torch.float32 and emb.dim() == 2)
+    if not ok:
+        loss = l1_loss_segmap_fused(render_dhw, seg_hw, emb, mask_hw)
+        loss.backward()
+        return loss.detach()
+    ctx = h.ctx
+    width, height, D, N = ctx.dims
+    if seg_hw.shape != (height, width) or emb.shape[1] != D:
+        raise ValueError("seg must be int32 [H,W] and emb float32 [n_seg, D]")
+    _C.require_cuda(seg_hw, emb)
+    dev = r.device
+    sg, em = seg_hw.contiguous(), emb.contiguous()
+    m = mask_hw.to(torch.float32).contiguous().reshape(-1) if mask_hw is not None else None
+    need_col = h.cols.requires_grad
+    _mark("bwd_start")
+    v_colors, sink = _take_grad_buffer(ctx, True, False, N, D, dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    _mark("bwd_zero")
+    cache = ctx.lease.bufs
+    numel = float(height * width * D)
+    _C.check(_C.lib.gags_blend_bwd_features_cached_l1(
+        D, width, height, _C.ptr(h.offsets), _C.ptr(cache[0]), _C.ptr(cache[1]), _C.ptr(cache[2]),
+        _C.ptr(cache[3]), _C.ptr(r), _C.ptr(sg), _C.ptr(em), _C.ptr(m), em.shape[0], 1.0 / numel,
+        _C.ptr(loss), _C.ptr(v_colors), _C.stream_ptr()), "gags_blend_bwd_features_cached_l1")
+    _C.count_launch((D + 255) // 256)
+    _mark("blend_bwd")
+    # this view's weight tiles are spent: hand the buffers back before the next forward
+    ctx.lease = None
+    render_dhw._gags_fused = None
+    if sink is not None:
+        if sink.grad is None:
+            sink.grad = v_colors
+    elif need_col:
+        cols = h.cols
+        if cols.is_leaf:
+            # what AccumulateGrad does with a gradient nobody else holds: adopt it (no 2 GB copy)
+            if cols.grad is None:
+                cols.grad = v_colors
+            else:
+                cols.grad.add_(v_colors)
+        else:
+            torch.autograd.backward([cols], [v_colors])  # through whatever produced the features
+    return loss[0] / numel
+
+
 class _Blend(torch.autograd.Function):
     """means2d / conics / opac are the differentiable handles of the projection outputs; the
     kernels read the same values from the packed `geom` record."""
@@ -415,16 +518,19 @@ class _Blend(torch.autograd.Function):
         # pure HBM stream, the forward above is instruction-bound with its shared memory full: the
         # fill runs beside it on the side stream instead of in front of the backward.
         ctx.prezero = None
-        if cache is not None and lookahead and stage_events is None:
+        if (cache is not None and prezero_overlap and stage_events is None
+                and not (ctx.sink is not None and ctx.sink.grad is not None)):
             main = torch.cuda.current_stream(dev)
-            side = _side_state(dev)["stream"]
-            with torch.cuda.stream(side):
+            zs = _zero_stream(dev)
+            with torch.cuda.stream(zs):
                 vz = torch.zeros(N, D, dtype=torch.float32, device=dev)   # fill kernel: 0.27 ms
                 # (cudaMemsetAsync — gags_memset_zero — measured 0.33 ms for the same 2 GB)
                 evz = torch.cuda.Event()
-                evz.record(side)
+                evz.record(zs)
             ctx.prezero = (vz, evz, main)
         ctx.lease = lease if cache is not None else None
+        global _last_cached_ctx
+        _last_cached_ctx = ctx if cache is not None else None
         ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
         ctx.mark_non_differentiable(last_ids)
         return render, alphas, last_ids
@@ -442,19 +548,7 @@ class _Blend(torch.autograd.Function):
         v_render = _f32c(v_render)
         st = _C.stream_ptr()
         _mark("bwd_start")
-        sink = ctx.sink if (need_col and not need_geo) else None
-        if sink is not None and sink.grad is not None and sink.grad.is_contiguous() \
-                and sink.grad.dtype == torch.float32:
-            v_colors = sink.grad                     # accumulate in place: nothing to zero or add
-            ctx.prezero = None
-        elif need_col and ctx.prezero is not None:
-            v_colors, evz, _ = ctx.prezero
-            cur = torch.cuda.current_stream(dev)
-            cur.wait_event(evz)
-            v_colors.record_stream(cur)
-            ctx.prezero = None
-        else:
-            v_colors = torch.zeros(N, D, device=dev) if need_col else None
+        v_colors, sink = _take_grad_buffer(ctx, need_col, need_geo, N, D, dev)
         _mark("bwd_zero")
         v_m = v_c = v_o = v_bg = None
         if not need_geo:
@@ -575,6 +669,12 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
                                             binned["offsets"], binned["flatten_ids"], width, height)
     _mark("blend_fwd")
+    global _last_cached_ctx
+    if _last_cached_ctx is not None:
+        if not pad and render_mode == "RGB":
+            render._gags_fused = _FusedHandle(_last_cached_ctx, cols, binned["offsets"],
+                                              render.data_ptr())
+        _last_cached_ctx = None
     if use_side:
         ss["ev_prev"] = torch.cuda.Event()
         ss["ev_prev"].record(main)

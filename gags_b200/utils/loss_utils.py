@@ -84,3 +84,10 @@ def l1_loss_segmap_fused(render_dhw, seg_hw, emb, mask_hw=None):
     reference gathers into a [D,H,W] map every iteration before the loss (train.py:162-163).  The
     mean is over all H*W*D elements, as l1_loss does."""
     return _L1Fused.apply(render_dhw.permute(1, 2, 0), None, mask_hw, seg_hw, emb)
+
+
+def l1_backward_fused(render_dhw, seg_hw, emb, mask_hw=None):
+    """`loss = l1_loss_segmap_fused(...); loss.backward()` as ONE call that never materialises the
+    [H,W,D] loss gradient (rasterization.fused_l1_backward); returns the detached loss."""
+    from ..rasterization import fused_l1_backward
+    return fused_l1_backward(render_dhw, seg_hw, emb, mask_hw)

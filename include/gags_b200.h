@@ -191,6 +191,18 @@ int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
                                    const int32_t *wmeta, const int32_t *wlist,
                                    int32_t *wcount, const float *v_render, float *v_colors,
                                    void *stream);
+/* The same backward with the masked L1 loss of train.py:162-163 fused into it: takes the RENDER
+ * instead of v_render, forms v_render = grad_scale * m * sign(render - emb[seg]) on the fly (the
+ * semantics of gags_l1_loss_segmap below; seg < 0 or >= n_seg = pixel without a target; mask may be
+ * NULL) and adds sum m |render - emb[seg]| to *loss_out (caller zeroes it and divides by H W D).
+ * Replaces the pair gags_l1_loss_segmap + gags_blend_bwd_features_cached: the [H,W,D] gradient map
+ * is never written to or read from HBM.                                                         */
+int gags_blend_bwd_features_cached_l1(int32_t D, int32_t width, int32_t height,
+                                      const int32_t *offsets, const void *wcache,
+                                      const int32_t *wmeta, const int32_t *wlist, int32_t *wcount,
+                                      const float *render, const int32_t *seg, const float *emb,
+                                      const float *mask, int32_t n_seg, float grad_scale,
+                                      float *loss_out, float *v_colors, void *stream);
 
 /* K8b full backward (replaces rasterize_to_pixels_bwd; App. A.6).  Outputs must be
  * zero-initialised; v_colors may be NULL (skip), v_alphas may be NULL (= 0).  D <= 256.

@@ -598,3 +598,81 @@ def test_gsplat_shaped_entry_point():
     ref, _, _ = O.rasterization(d["means"], d["quats"], d["scales"], d["opacities"], d["colors"],
                                 d["viewmat"], d["K"], 64, 48, torch.zeros(8, dtype=torch.float64))
     assert frac_bad(colors[0], ref, 1e-3) < 2e-3
+
+
+@pytest.mark.parametrize("H,W,D,with_mask,direct", [(96, 160, 64, False, False),
+                                                    (75, 131, 256, True, False),
+                                                    (64, 96, 128, False, True)])
+def test_fused_l1_backward_equals_loss_then_backward(H, W, D, with_mask, direct):
+    """fused_l1_backward (loss gradient formed inside the cached backward) == l1_loss_segmap_fused +
+    loss.backward(): same loss, same feature gradient — pixels without a target (seg < 0), a mask,
+    image sizes that are not tile multiples and half tiles without any Gaussian included."""
+    from gags_b200 import rasterization as R
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_loss_segmap_fused, l1_backward_fused
+    dev = torch.device("cuda:0")
+    scene = make_scene(3000, H, W, D, seed=11, n_views=4, sigma_px_median=1.5)
+    scene.xyz[:, 0] = scene.xyz[:, 0].abs()            # one side of the image stays empty
+    g = torch.Generator().manual_seed(9)
+    S = 13
+    seg = torch.randint(-1, S, (H, W), generator=g, dtype=torch.int32).to(dev)
+    emb = (0.2 * torch.randn(S, D, generator=g)).to(dev)
+    mask = torch.rand(H, W, generator=g).to(dev) if with_mask else None
+    bg = torch.zeros(3, device=dev)
+    out = []
+    try:
+        R.direct_grad_accumulation = direct
+        for fused in (False, True):
+            pc = GaussianModel(3, device=dev)
+            pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                                   scene.features_dc, scene.features_rest, scene.semantic_feature)
+            pc.training_setup(OptimizationParams(), fused_optimizer=True)
+            losses = []
+            for v in (0, 1):                              # two views accumulate into one .grad
+                pkg = render(scene.cameras[v].to(dev), pc, None, bg)
+                if fused:
+                    assert getattr(pkg["render"], "_gags_fused", None) is not None
+                    losses.append(float(l1_backward_fused(pkg["render"], seg, emb, mask)))
+                else:
+                    loss = l1_loss_segmap_fused(pkg["render"], seg, emb, mask)
+                    loss.backward()
+                    losses.append(float(loss))
+            torch.cuda.synchronize()
+            out.append((losses, pc._semantic_feature.grad.clone()))
+    finally:
+        R.direct_grad_accumulation = False
+    (l0, g0), (l1, g1) = out
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a)
+    assert float(g0.abs().max()) > 0
+    assert rel_err(g1, g0) < 2e-6
+
+
+def test_fused_l1_backward_falls_back_without_cache():
+    """a render that did not keep its weight tiles (narrow D) takes the two-kernel route."""
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_loss_segmap_fused, l1_backward_fused
+    dev = torch.device("cuda:0")
+    H, W, D = 48, 64, 16
+    scene = make_scene(500, H, W, D, seed=3, n_views=2, sigma_px_median=2.0)
+    seg = torch.zeros(H, W, dtype=torch.int32, device=dev)
+    emb = torch.full((1, D), 0.1, device=dev)
+    grads = []
+    for fused in (False, True):
+        pc = GaussianModel(3, device=dev)
+        pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                               scene.features_dc, scene.features_rest, scene.semantic_feature)
+        pc.training_setup(OptimizationParams(), fused_optimizer=True)
+        pkg = render(scene.cameras[0].to(dev), pc, None, torch.zeros(3, device=dev))
+        if fused:
+            l1_backward_fused(pkg["render"], seg, emb)
+        else:
+            l1_loss_segmap_fused(pkg["render"], seg, emb).backward()
+        grads.append(pc._semantic_feature.grad.clone())
+    assert rel_err(grads[1], grads[0]) < 2e-6

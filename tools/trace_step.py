@@ -11,7 +11,7 @@ from gags_b200.arguments import OptimizationParams
 from gags_b200.gaussian_renderer import render
 from gags_b200.scene import GaussianModel
 from gags_b200.synthetic import config_scene
-from gags_b200.utils.loss_utils import l1_loss_segmap_fused
+from gags_b200.utils.loss_utils import l1_loss_segmap_fused, l1_backward_fused
 dev = torch.device("cuda:0")
 scene = config_scene(3)
 pc = GaussianModel(3, device=dev)
@@ -26,8 +26,11 @@ seg = torch.randint(0, 256, (1080, 1920), generator=g, dtype=torch.int32).to(dev
 emb = (0.1 * torch.randn(256, 256, generator=g)).to(dev)
 def step(i):
     pkg = render(cams[i % 64], pc, None, bg)
-    loss = l1_loss_segmap_fused(pkg["render"], seg, emb)
-    loss.backward()
+    if os.environ.get("UNFUSED_LOSS"):
+        loss = l1_loss_segmap_fused(pkg["render"], seg, emb)
+        loss.backward()
+    else:
+        l1_backward_fused(pkg["render"], seg, emb)
     pc.optimizer.step()
     pc.optimizer.zero_grad(set_to_none=True)
 for i in range(10): step(i)

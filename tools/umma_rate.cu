@@ -145,6 +145,19 @@ __global__ void __launch_bounds__(128) probe(const float *V, const float *W, flo
                     make_desc(smem_u32(sV1) + ks * 2048, 4096, 1024), f256, 1);
         continue;
       }
+      if (mode == 3 || mode == 4) {
+        // transposed forward: 12 MMAs N=128; mode 3 = MN-major A (feature tile), mode 4 = K-major A
+        const uint32_t id = IDESC_BASE | ((mode == 3 ? 1u : 0u) << 15) | ((128u >> 3) << 17) |
+                            ((128u >> 4) << 24);
+        for (int ks = 0; ks < 2; ++ks)
+          for (int mb = 0; mb < 2; ++mb)
+            for (int q = 0; q < 3; ++q) {
+              const uint64_t a = mode == 3 ? make_desc(smem_u32(sV1) + mb * 8192 + ks * 2048, 4096, 1024)
+                                           : make_desc(smem_u32(sV1) + mb * 16384 + ks * 32, 16, 1024);
+              umma_ss(tb + mb * 128, a, make_desc(smem_u32(sW1) + ks * 32, 16, 1024), id, 1);
+            }
+        continue;
+      }
       // W tile = [hi(32 g) | lo(32 g)] per pixel row: N=64 covers both halves, N=32 the hi half
       for (int ks = 0; ks < 8; ++ks) {
         const uint64_t bw = make_desc(smem_u32(sW1) + ks * 2048, 16, 1024);
@@ -164,7 +177,7 @@ __global__ void __launch_bounds__(128) probe(const float *V, const float *W, flo
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (mode != 2) {
+  if (mode < 2) {
     for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c0, r);
@@ -212,8 +225,9 @@ int main() {
     printf("mode %d (%s): max abs err %.3e (max |ref| %.3f, rel %.3e)\n", mode, mode ? "A in TMEM" : "A in smem",
            maxerr, maxref, maxerr / maxref);
   }
-  const char *names[3] = {"bwdS (A smem)", "bwdT (A tmem)", "fwd (6 x N=256)"};
-  for (int mode = 0; mode < 3; ++mode)
+  const char *names[5] = {"bwdS (A smem)", "bwdT (A tmem)", "fwd (6 x N=256)", "fwdT A mn (12xN128)",
+                          "fwdT A k (12xN128)"};
+  for (int mode = 0; mode < 5; ++mode)
     for (int reps : {1, 16, 64}) {
       probe<<<1, 128, 98304 + 1024>>>(dV, dW, dD, mode, reps, dC);
       CK(cudaDeviceSynchronize());
