@@ -55,6 +55,7 @@ SIGNATURES = {
     "gags_tile_bucket_max": (_i32, []),
     "gags_tile_bucket_count": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p]),
     "gags_tile_bucket_sort": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _p]),
+    "gags_tile_bucket_sort_guarded": (C.c_int, [_p, _i32, _i32, _p, _i64, _p, _p, _p]),
     "gags_sort_pairs_workspace_bytes": (_sz, [_i64]),
     "gags_sort_pairs": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _sz, C.POINTER(_i32), _p]),
     "gags_tile_offsets": (C.c_int, [_p, _i64, _i32, _p, _p]),

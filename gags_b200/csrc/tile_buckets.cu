@@ -184,7 +184,7 @@ __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int c
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ offsets,
+bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ offsets, long long cap,
                    long long *__restrict__ isect_ids, int *__restrict__ flatten_ids) {
   using Sort16 = cub::BlockRadixSort<unsigned, SORT_THREADS, 16, unsigned, 6>;
   constexpr int kSmem = sizeof(typename Sort16::TempStorage) > SORT_THREADS * 16 * 8
@@ -195,6 +195,9 @@ bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ off
   const int tile = blockIdx.x;
   const int s = offsets[tile], cnt = offsets[tile + 1] - s;
   if (cnt <= 0) return;
+  // speculative launch (before the host has read the counts): leave tiles alone that do not fit
+  // the slab or the output arrays — the caller sees the counts and redoes the view
+  if (cnt > BUCKET_MAX || (long long)s + cnt > cap) return;
   if (threadIdx.x == 0) { s_u[0] = 0u; s_u[1] = 0xffffffffu; s_u[2] = 0u; }
   __syncthreads();
   const uint2 *src = bucket + (size_t)tile * BUCKET_MAX;
@@ -247,8 +250,25 @@ extern "C" int gags_tile_bucket_sort(const void *bucket, int32_t tile_w, int32_t
   if (!bucket || !offsets || !flatten_ids || tile_w <= 0 || tile_h <= 0) return GAGS_EINVAL;
   if (max_bucket > BUCKET_MAX) return GAGS_ERANGE;
   bucket_sort_kernel<<<tile_w * tile_h, SORT_THREADS, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint2 *>(bucket), offsets, reinterpret_cast<long long *>(isect_ids),
-      flatten_ids);
+      reinterpret_cast<const uint2 *>(bucket), offsets, 0x7fffffffffffffffLL,
+      reinterpret_cast<long long *>(isect_ids), flatten_ids);
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+// The same sort launched BEFORE the host has read stats_dev (so the device sorts while the host
+// waits for the counts): `capacity` = elements the output arrays hold.  Tiles that overflow the slab
+// or the arrays are skipped on the device; the caller must check stats_dev afterwards and, if
+// n_isects > capacity or the largest bucket > gags_tile_bucket_max(), discard the result.
+extern "C" int gags_tile_bucket_sort_guarded(const void *bucket, int32_t tile_w, int32_t tile_h,
+                                             const int32_t *offsets, int64_t capacity,
+                                             int64_t *isect_ids, int32_t *flatten_ids,
+                                             void *stream) {
+  if (!bucket || !offsets || !flatten_ids || tile_w <= 0 || tile_h <= 0 || capacity < 0)
+    return GAGS_EINVAL;
+  bucket_sort_kernel<<<tile_w * tile_h, SORT_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint2 *>(bucket), offsets, (long long)capacity,
+      reinterpret_cast<long long *>(isect_ids), flatten_ids);
   GAGS_CHECK_LAUNCH();
   return 0;
 }

@@ -104,6 +104,18 @@ prezero_overlap = _os.environ.get("GAGS_B200_PREZERO", "1") != "0"
 _zero_streams: Dict = {}
 
 
+_readback: Dict = {}
+
+
+def _readback_state(dev):
+    """(copy stream, pinned 2-int buffer) for the n_isects readback beside a running sort."""
+    st = _readback.get(dev.index)
+    if st is None:
+        st = _readback[dev.index] = (torch.cuda.Stream(device=dev, priority=-1),
+                                     torch.empty(2, dtype=torch.int32).pin_memory())
+    return st
+
+
 def _zero_stream(dev):
     s = _zero_streams.get(dev.index)
     if s is None:
@@ -295,6 +307,8 @@ _isect_capacity = 0
 # passes), so the global path stays the default; the bucketed one moves a fifth of the bytes and
 # is the better neighbour for kernels running beside it.
 bucket_sort = True
+# enqueue the bucket sort before the n_isects readback once a capacity is known (see bin_and_sort)
+speculative_sort = True
 
 
 @torch.no_grad()
@@ -320,11 +334,39 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
                                                _C.ptr(offsets), _C.ptr(stats), st),
                  "gags_tile_bucket_count")
         _C.count_launch(2)
-        n, max_bucket = (int(v) for v in stats.tolist())      # the one host sync of the pipeline
+        # With a capacity known from earlier views the sort is enqueued BEFORE the counts are read
+        # back, so the device sorts during the host round trip; its guard skips tiles that do not
+        # fit, and the (rare) view that outgrew the capacity is sorted again below.
+        keys = vals = None
+        spec_cap = _isect_capacity if (speculative_sort and after_count is None) else 0
+        if spec_cap > 0:
+            main = torch.cuda.current_stream(dev)
+            ev_counts = torch.cuda.Event()
+            ev_counts.record(main)                            # counts + scan done
+            keys = torch.empty(spec_cap, dtype=torch.int64, device=dev)
+            vals = torch.empty(spec_cap, dtype=torch.int32, device=dev)
+            _C.check(_C.lib.gags_tile_bucket_sort_guarded(_C.ptr(bucket), tile_w, tile_h,
+                                                          _C.ptr(offsets), spec_cap, _C.ptr(keys),
+                                                          _C.ptr(vals), st),
+                     "gags_tile_bucket_sort_guarded")
+            _C.count_launch(1)
+            # the readback goes through a second stream that waits for the scan only, not the sort
+            cs, pinned = _readback_state(dev)
+            cs.wait_event(ev_counts)
+            with torch.cuda.stream(cs):
+                pinned.copy_(stats, non_blocking=True)
+            stats.record_stream(cs)
+            cs.synchronize()                                  # the one host sync of the pipeline
+            n, max_bucket = (int(v) for v in pinned.tolist())
+        else:
+            n, max_bucket = (int(v) for v in stats.tolist())  # the one host sync of the pipeline
         if after_count is not None:
             after_count()
             after_count = None
         if max_bucket <= bmax:
+            if spec_cap > 0 and n <= spec_cap:
+                return dict(n_isects=n, isect_ids=keys[:n], flatten_ids=vals[:n], offsets=offsets,
+                            cum_tiles=None, _bases=(keys, vals, offsets))
             if n > _isect_capacity:
                 _isect_capacity = int(n * 1.2) + 1024
             cap = _isect_capacity

@@ -137,6 +137,12 @@ int gags_tile_bucket_count(const float *means2d, const int32_t *radii, const flo
 int gags_tile_bucket_sort(const void *bucket, int32_t tile_w, int32_t tile_h, const int32_t *offsets,
                           int32_t max_bucket, int64_t *isect_ids, int32_t *flatten_ids,
                           void *stream);
+/* gags_tile_bucket_sort launched before the host has read stats_dev (the device sorts while the
+ * host waits for the counts).  capacity = elements isect_ids / flatten_ids hold; tiles that do not
+ * fit are skipped on the device and the caller discards the result when stats_dev says so.      */
+int gags_tile_bucket_sort_guarded(const void *bucket, int32_t tile_w, int32_t tile_h,
+                                  const int32_t *offsets, int64_t capacity, int64_t *isect_ids,
+                                  int32_t *flatten_ids, void *stream);
 
 /* K5  stable LSD radix sort of (int64 key, int32 value) on bits [0, end_bit)
  * (replaces gsplat's cub::DeviceRadixSort::SortPairs call).  Ping-pong buffers: the result is in

@@ -109,6 +109,28 @@ def test_tile_stage_is_bit_exact(seed, n, w, h, bucketed):
     assert int(st["offsets"][-1]) == keys.numel()
 
 
+@pytest.mark.parametrize("cap0", [0, 100, 10_000_000])
+def test_speculative_bucket_sort_matches_oracle(cap0):
+    """the bucket sort enqueued before the n_isects readback: no capacity yet (plain path), a
+    capacity the view outgrows (guard skips, the view is sorted again) and an ample one — all give
+    the oracle's arrays; a second call then runs on the capacity the first one left."""
+    from gags_b200 import rasterization as R
+    sc = front_scene(6000, 200, 120, 3, seed=21, sigma_px=(0.5, 12.0))
+    old = R._isect_capacity
+    try:
+        R._isect_capacity = cap0
+        runs = [_stages(sc), _stages(sc)]
+        assert R._isect_capacity >= runs[0]["n_isects"]
+    finally:
+        R._isect_capacity = max(old, R._isect_capacity)
+    m2d, radii, dep = runs[0]["means2d"].cpu(), runs[0]["radii"].cpu(), runs[0]["depths"].cpu()
+    _, keys, vals = O.isect_tiles(m2d, radii, dep, runs[0]["tw"], runs[0]["th"])
+    for st in runs:
+        assert st["n_isects"] == keys.numel()
+        assert torch.equal(st["isect_ids"].cpu(), keys)
+        assert torch.equal(st["flatten_ids"].cpu(), vals)
+
+
 def test_tile_count_standalone_and_empty():
     from gags_b200 import _C
     sc = front_scene(1000, 96, 64, 3, seed=8)
