@@ -23,54 +23,73 @@
 
 namespace {
 
-constexpr int COOP = 32;
 constexpr int SORT_THREADS = 256;
 constexpr int BUCKET_MAX = SORT_THREADS * 16;
 
-// visits every tile of every Gaussian: small footprints per thread, large ones by the whole warp
-template <class F>
-__device__ __forceinline__ void for_each_tile(const float2 *__restrict__ means2d,
-                                              const int *__restrict__ radii, long long N, int tile_w,
-                                              int tile_h, F f) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int x0 = 0, x1 = 0, y0 = 0, y1 = 0, cnt = 0;
-  if (i < N && radii[i] > 0) {
-    const float2 m = means2d[i];
-    tile_bounds(m.x, m.y, radii[i], tile_w, tile_h, x0, x1, y0, y1);
-    cnt = (x1 - x0) * (y1 - y0);
-  }
-  if (cnt > 0 && cnt < COOP) {
-    for (int ty = y0; ty < y1; ++ty)
-      for (int tx = x0; tx < x1; ++tx) f(ty * tile_w + tx, i);
-  }
-  unsigned big = __ballot_sync(0xffffffffu, cnt >= COOP);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const int bx0 = __shfl_sync(0xffffffffu, x0, src);
-    const int bx1 = __shfl_sync(0xffffffffu, x1, src);
-    const int by0 = __shfl_sync(0xffffffffu, y0, src);
-    const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
-    const long long gid = i - lane + src;
-    const int nx = bx1 - bx0;
-    for (int k = lane; k < bcnt; k += 32) f((by0 + k / nx) * tile_w + bx0 + k % nx, gid);
-  }
-}
-
 // steps 1+3 fused: slot = cursor[t]++ ; the tile's bucket is the fixed-capacity slab
 // bucket[t * BUCKET_MAX ...] (entries beyond the capacity are dropped; the caller sees the count and
-// falls back to the global sort), so no histogram pass is needed before the scatter
+// falls back to the global sort), so no histogram pass is needed before the scatter.
+//
+// The kernel is bound by the latency of the returning atomic (ncu: 84 % of the stall samples wait
+// for it), so the (Gaussian, tile) pairs of a warp are spread evenly over its lanes — a warp scan
+// of the per-Gaussian tile counts, then lane l takes pairs l, l + 32, ... and finds each pair's
+// Gaussian by a 5-step search over the scanned counts — and every lane keeps SCATTER_ILP atomics in
+// flight before it touches the first result.  A warp with 32 small footprints thus needs
+// sum/64 round trips instead of max(count).
+constexpr int SCATTER_ILP = 2;
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii,
                     const float *__restrict__ depths, long long N, int tile_w, int tile_h,
                     int *__restrict__ cursor, uint2 *__restrict__ bucket) {
-  for_each_tile(means2d, radii, N, tile_w, tile_h, [&](int t, long long gid) {
-    const int slot = atomicAdd(cursor + t, 1);
-    if (slot < BUCKET_MAX)
-      bucket[(size_t)t * BUCKET_MAX + slot] =
-          make_uint2(__float_as_uint(__ldg(depths + gid)), (unsigned)gid);
-  });
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, nx = 0, y0 = 0, cnt = 0;
+  unsigned dbits = 0u;
+  if (i < N && radii[i] > 0) {
+    const float2 m = means2d[i];
+    int x1, y1;
+    tile_bounds(m.x, m.y, radii[i], tile_w, tile_h, x0, x1, y0, y1);
+    nx = x1 - x0;
+    cnt = nx * (y1 - y0);
+    dbits = __float_as_uint(__ldg(depths + i));
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  const int excl = incl - cnt;
+  const unsigned gid0 = (unsigned)(i - lane);
+  for (int k0 = 0; k0 < total; k0 += 32 * SCATTER_ILP) {
+    int tile[SCATTER_ILP], slot[SCATTER_ILP];
+    uint2 rec[SCATTER_ILP];
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u) {
+      const int k = k0 + u * 32 + lane;
+      // owner = the last lane whose exclusive count is <= k (lanes without tiles never win: the
+      // next lane with tiles has the same exclusive count and a larger index)
+      int src = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int e = __shfl_sync(FULL, excl, (src + step) & 31);
+        if (e <= k) src += step;
+      }
+      const int local = k - __shfl_sync(FULL, excl, src);
+      const int ox0 = __shfl_sync(FULL, x0, src), oy0 = __shfl_sync(FULL, y0, src);
+      const int onx = max(1, __shfl_sync(FULL, nx, src));
+      rec[u] = make_uint2(__shfl_sync(FULL, dbits, src), gid0 + (unsigned)src);
+      const int row = local / onx;
+      tile[u] = k < total ? (oy0 + row) * tile_w + ox0 + (local - row * onx) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u) slot[u] = tile[u] >= 0 ? atomicAdd(cursor + tile[u], 1) : 0;
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u)
+      if (tile[u] >= 0 && slot[u] < BUCKET_MAX) bucket[(size_t)tile[u] * BUCKET_MAX + slot[u]] = rec[u];
+  }
 }
 
 // single CTA: exclusive scan of count[n_tiles] -> offsets[n_tiles + 1]; stats = {n_isects, max}
@@ -183,18 +202,25 @@ __device__ __forceinline__ void sort_bucket(const uint2 *__restrict__ src, int c
   }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+// Two register classes, two launches over the same grid (a CTA whose tile belongs to the other class
+// leaves at once): the 16-items-per-thread variant needs 126 registers, which held every tile to two
+// CTAs per SM although the typical tile (~1200 intersections at config 3) sorts with 5-8 per thread.
+constexpr int SMALL_ITEMS = 8;
+template <bool LARGE>
+__global__ void __launch_bounds__(SORT_THREADS, LARGE ? 2 : 3)
 bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ offsets, long long cap,
                    long long *__restrict__ isect_ids, int *__restrict__ flatten_ids) {
-  using Sort16 = cub::BlockRadixSort<unsigned, SORT_THREADS, 16, unsigned, 6>;
-  constexpr int kSmem = sizeof(typename Sort16::TempStorage) > SORT_THREADS * 16 * 8
-                            ? (int)sizeof(typename Sort16::TempStorage)
-                            : SORT_THREADS * 16 * 8;
+  constexpr int MAXI = LARGE ? 16 : SMALL_ITEMS;
+  using SortMax = cub::BlockRadixSort<unsigned, SORT_THREADS, MAXI, unsigned, 6>;
+  constexpr int kSmem = sizeof(typename SortMax::TempStorage) > SORT_THREADS * MAXI * 8
+                            ? (int)sizeof(typename SortMax::TempStorage)
+                            : SORT_THREADS * MAXI * 8;
   __shared__ __align__(16) unsigned char smem[kSmem];
   __shared__ unsigned s_u[3];                     // tie flag, smallest key, largest key
   const int tile = blockIdx.x;
   const int s = offsets[tile], cnt = offsets[tile + 1] - s;
   if (cnt <= 0) return;
+  if ((cnt > SORT_THREADS * SMALL_ITEMS) != LARGE) return;
   // speculative launch (before the host has read the counts): leave tiles alone that do not fit
   // the slab or the output arrays — the caller sees the counts and redoes the view
   if (cnt > BUCKET_MAX || (long long)s + cnt > cap) return;
@@ -203,12 +229,27 @@ bucket_sort_kernel(const uint2 *__restrict__ bucket, const int *__restrict__ off
   const uint2 *src = bucket + (size_t)tile * BUCKET_MAX;
   long long *ko = isect_ids ? isect_ids + s : nullptr;
   int *io = flatten_ids + s;
-  if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, ko, io, smem, s_u);
-  else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, ko, io, smem, s_u);
-  else if (cnt <= SORT_THREADS * 5) sort_bucket<5>(src, cnt, tile, ko, io, smem, s_u);
-  else if (cnt <= SORT_THREADS * 6) sort_bucket<6>(src, cnt, tile, ko, io, smem, s_u);
-  else if (cnt <= SORT_THREADS * 8) sort_bucket<8>(src, cnt, tile, ko, io, smem, s_u);
-  else sort_bucket<16>(src, cnt, tile, ko, io, smem, s_u);
+  if constexpr (LARGE) {
+    if (cnt <= SORT_THREADS * 11) sort_bucket<11>(src, cnt, tile, ko, io, smem, s_u);
+    else sort_bucket<16>(src, cnt, tile, ko, io, smem, s_u);
+  } else {
+    if (cnt <= SORT_THREADS * 2) sort_bucket<2>(src, cnt, tile, ko, io, smem, s_u);
+    else if (cnt <= SORT_THREADS * 4) sort_bucket<4>(src, cnt, tile, ko, io, smem, s_u);
+    else if (cnt <= SORT_THREADS * 5) sort_bucket<5>(src, cnt, tile, ko, io, smem, s_u);
+    else if (cnt <= SORT_THREADS * 6) sort_bucket<6>(src, cnt, tile, ko, io, smem, s_u);
+    else sort_bucket<8>(src, cnt, tile, ko, io, smem, s_u);
+  }
+}
+
+int launch_bucket_sort(const void *bucket, int n_tiles, const int *offsets, long long cap,
+                       int64_t *isect_ids, int32_t *flatten_ids, cudaStream_t st) {
+  bucket_sort_kernel<false><<<n_tiles, SORT_THREADS, 0, st>>>(
+      reinterpret_cast<const uint2 *>(bucket), offsets, cap, reinterpret_cast<long long *>(isect_ids),
+      flatten_ids);
+  bucket_sort_kernel<true><<<n_tiles, SORT_THREADS, 0, st>>>(
+      reinterpret_cast<const uint2 *>(bucket), offsets, cap, reinterpret_cast<long long *>(isect_ids),
+      flatten_ids);
+  return (int)cudaGetLastError();
 }
 
 }  // namespace
@@ -249,11 +290,8 @@ extern "C" int gags_tile_bucket_sort(const void *bucket, int32_t tile_w, int32_t
                                      int32_t *flatten_ids, void *stream) {
   if (!bucket || !offsets || !flatten_ids || tile_w <= 0 || tile_h <= 0) return GAGS_EINVAL;
   if (max_bucket > BUCKET_MAX) return GAGS_ERANGE;
-  bucket_sort_kernel<<<tile_w * tile_h, SORT_THREADS, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint2 *>(bucket), offsets, 0x7fffffffffffffffLL,
-      reinterpret_cast<long long *>(isect_ids), flatten_ids);
-  GAGS_CHECK_LAUNCH();
-  return 0;
+  return launch_bucket_sort(bucket, tile_w * tile_h, offsets, 0x7fffffffffffffffLL, isect_ids,
+                            flatten_ids, (cudaStream_t)stream);
 }
 
 // The same sort launched BEFORE the host has read stats_dev (so the device sorts while the host
@@ -266,9 +304,6 @@ extern "C" int gags_tile_bucket_sort_guarded(const void *bucket, int32_t tile_w,
                                              void *stream) {
   if (!bucket || !offsets || !flatten_ids || tile_w <= 0 || tile_h <= 0 || capacity < 0)
     return GAGS_EINVAL;
-  bucket_sort_kernel<<<tile_w * tile_h, SORT_THREADS, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint2 *>(bucket), offsets, (long long)capacity,
-      reinterpret_cast<long long *>(isect_ids), flatten_ids);
-  GAGS_CHECK_LAUNCH();
-  return 0;
+  return launch_bucket_sort(bucket, tile_w * tile_h, offsets, (long long)capacity, isect_ids,
+                            flatten_ids, (cudaStream_t)stream);
 }

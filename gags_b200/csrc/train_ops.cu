@@ -251,6 +251,38 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   return 0;
 }
 
+// Zero-fill with a SMALL grid (two 256-thread CTAs per SM): stores are fire-and-forget, so a quarter
+// of the thread slots already streams at HBM rate, and the other three quarters stay free for the
+// latency-bound kernels this fill is meant to run beside (projection / tile scatter / bucket sort at
+// the start of a view; torch's fill kernel and cudaMemsetAsync both occupy every slot and simply
+// push those kernels behind them).
+__global__ void __launch_bounds__(256)
+zero_fill_kernel(float4 *__restrict__ p, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    p[i] = z;
+    p[i + stride] = z;
+    p[i + 2 * stride] = z;
+    p[i + 3 * stride] = z;
+  }
+  for (; i < n4; i += stride) p[i] = z;
+}
+
+extern "C" int gags_zero_fill(void *ptr, int64_t bytes, void *stream) {
+  if ((!ptr && bytes) || bytes < 0) return GAGS_EINVAL;
+  if (bytes == 0) return 0;
+  if (!gags_aligned16(ptr) || (bytes & 15)) return GAGS_EALIGN;
+  const long long n4 = bytes / 16;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 2) blocks = 148LL * 2;
+  zero_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4 *>(ptr), n4);
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
 // Zero-fill through cudaMemsetAsync (a driver memset, not one of this library's kernels): used for
 // the 2 GB gradient accumulation buffer so that the fill does not compete for SM slots with the
 // kernels running on the other stream.

@@ -116,6 +116,43 @@ def _readback_state(dev):
     return st
 
 
+_pending_prezero = None
+
+
+def _early_prezero(colors, geo_in, sh_degree) -> None:
+    """Start zeroing the backward's [N, D] accumulation buffer at the very beginning of the view,
+    on its own stream: the projection / scatter / sort kernels in front of the blend are latency
+    bound and leave HBM idle, whereas the forward and backward blends fill the register file and
+    the optimiser pass is HBM bound — nothing can run in THEIR shadow (measured: a fill launched
+    right behind the forward starts when the forward drains)."""
+    global _pending_prezero
+    _pending_prezero = None
+    if not (prezero_overlap and stage_events is None and weight_cache and sh_degree is None
+            and torch.is_grad_enabled() and colors.is_cuda and colors.requires_grad
+            and colors.dim() == 2 and not any(t.requires_grad for t in geo_in)):
+        return
+    N, D = colors.shape
+    if not _C.lib.gags_blend_cache_supported(D):
+        return
+    if (direct_grad_accumulation and colors.is_leaf and colors.grad is not None):
+        return                                        # the backward will reduce straight into .grad
+    dev = colors.device
+    zs = _zero_stream(dev)
+    # not earlier than the main stream gets here (the host runs a view ahead of the device and the
+    # fill would otherwise land between the previous view's blends)
+    ev0 = torch.cuda.Event()
+    ev0.record(torch.cuda.current_stream(dev))
+    zs.wait_event(ev0)
+    with torch.cuda.stream(zs):
+        vz = torch.empty(N, D, dtype=torch.float32, device=dev)
+        _C.check(_C.lib.gags_zero_fill(_C.ptr(vz), vz.numel() * 4, zs.cuda_stream),
+                 "gags_zero_fill")                    # small-grid fill: leaves the SMs' slots free
+        _C.count_launch()
+        evz = torch.cuda.Event()
+        evz.record(zs)
+    _pending_prezero = (vz, evz, torch.cuda.current_stream(dev))
+
+
 def _zero_stream(dev):
     s = _zero_streams.get(dev.index)
     if s is None:
@@ -560,16 +597,11 @@ class _Blend(torch.autograd.Function):
         # pure HBM stream, the forward above is instruction-bound with its shared memory full: the
         # fill runs beside it on the side stream instead of in front of the backward.
         ctx.prezero = None
-        if (cache is not None and prezero_overlap and stage_events is None
-                and not (ctx.sink is not None and ctx.sink.grad is not None)):
-            main = torch.cuda.current_stream(dev)
-            zs = _zero_stream(dev)
-            with torch.cuda.stream(zs):
-                vz = torch.zeros(N, D, dtype=torch.float32, device=dev)   # fill kernel: 0.27 ms
-                # (cudaMemsetAsync — gags_memset_zero — measured 0.33 ms for the same 2 GB)
-                evz = torch.cuda.Event()
-                evz.record(zs)
-            ctx.prezero = (vz, evz, main)
+        global _pending_prezero
+        if cache is not None and _pending_prezero is not None \
+                and _pending_prezero[0].shape == (N, D):
+            ctx.prezero = _pending_prezero
+        _pending_prezero = None
         ctx.lease = lease if cache is not None else None
         global _last_cached_ctx
         _last_cached_ctx = ctx if cache is not None else None
@@ -645,6 +677,7 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     if 32 + tile_bits(tile_w * tile_h) > 64:
         raise ValueError("image too large for the 64-bit intersection key")
     geo_in = (means, quats, scales, opacities)
+    _early_prezero(colors, geo_in, sh_degree)
     use_side = (lookahead and stage_events is None and means.is_cuda and viewmat.is_cuda
                 and not any(t.requires_grad for t in geo_in))
     if use_side:

@@ -249,6 +249,10 @@ int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                    double lr, double beta1, double beta2, double eps, int32_t step,
                    int32_t zero_grad, void *stream);
 
+/* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
+ * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
+int gags_zero_fill(void *ptr, int64_t bytes, void *stream);
+
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (driver memset; keeps the 2 GB gradient-buffer fill off
  * the SMs that the neighbouring stream's kernels need). */
 int gags_memset_zero(void *ptr, size_t bytes, void *stream);
