@@ -35,8 +35,8 @@ constexpr int BUCKET_MAX = SORT_THREADS * 16;
 // of the per-Gaussian tile counts, then lane l takes pairs l, l + 32, ... and finds each pair's
 // Gaussian by a 5-step search over the scanned counts — and every lane keeps SCATTER_ILP atomics in
 // flight before it touches the first result.  A warp with 32 small footprints thus needs
-// sum/64 round trips instead of max(count).
-constexpr int SCATTER_ILP = 2;
+// sum/(32 SCATTER_ILP) round trips instead of max(count).
+constexpr int SCATTER_ILP = 4;
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const float2 *__restrict__ means2d, const int *__restrict__ radii,
                     const float *__restrict__ depths, long long N, int tile_w, int tile_h,

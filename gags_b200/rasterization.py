@@ -339,10 +339,9 @@ def tile_bits(n_tiles: int) -> int:
 _isect_capacity = 0
 # True = K4-K6 through the tile-bucketed segmented sort (csrc/tile_buckets.cu); False = count /
 # scan / emit / global cub radix sort / offsets (csrc/tiles.cu).  Both give identical arrays
-# (tests/test_gpu_parity.py::test_tile_stage_is_bit_exact).  Measured at config 3 on B200: 0.93 ms
-# bucketed (hist 0.14 + scatter 0.31 + 9-pass block sort 0.47) vs 0.89 ms global (6 onesweep
-# passes), so the global path stays the default; the bucketed one moves a fifth of the bytes and
-# is the better neighbour for kernels running beside it.
+# (tests/test_gpu_parity.py::test_tile_stage_is_bit_exact).  Measured at config 3 on B200: 0.57 ms
+# bucketed (scatter 0.21 + scan 0.01 + block sort 0.35) vs 0.89 ms global (6 onesweep passes); a
+# tile with more than gags_tile_bucket_max() intersections falls back to the global path.
 bucket_sort = True
 # enqueue the bucket sort before the n_isects readback once a capacity is known (see bin_and_sort)
 speculative_sort = True
