@@ -385,7 +385,7 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
                                                           _C.ptr(offsets), spec_cap, _C.ptr(keys),
                                                           _C.ptr(vals), st),
                      "gags_tile_bucket_sort_guarded")
-            _C.count_launch(1)
+            _C.count_launch(2)                                # small- and large-bucket launch
             # the readback goes through a second stream that waits for the scan only, not the sort
             cs, pinned = _readback_state(dev)
             cs.wait_event(ev_counts)
@@ -412,7 +412,7 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
                 _C.check(_C.lib.gags_tile_bucket_sort(_C.ptr(bucket), tile_w, tile_h,
                                                       _C.ptr(offsets), max_bucket, _C.ptr(keys),
                                                       _C.ptr(vals), st), "gags_tile_bucket_sort")
-                _C.count_launch(1)
+                _C.count_launch(2)
             return dict(n_isects=n, isect_ids=keys[:n], flatten_ids=vals[:n], offsets=offsets,
                         cum_tiles=None, _bases=(keys, vals, offsets))
         # a tile with more intersections than a CTA sorts in shared memory: global radix sort
