@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="override N (debug only; invalidates value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N>1: NCCL all-reduce + local Adam instead of the fused peer-memory step")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="separate L1 kernel + autograd backward instead of l1_backward_fused")
     return ap.parse_args()
@@ -145,7 +147,9 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    kviews = args.views_per_step or (1 if world == 1 else 4)
+    # one view per rank per optimiser step at every N (the train.py loop on each rank): per-GPU work
+    # is the same at 1, 2, 4 and 8 GPUs; --views-per-step k accumulates k views before the exchange
+    kviews = args.views_per_step or 1
 
     n, H, W, D = CONFIGS[args.config]
     scene = config_scene(args.config)
@@ -181,6 +185,27 @@ def main():
     # k views per optimiser step: let the backward reduce straight into .grad (see rasterization.py)
     R.direct_grad_accumulation = kviews > 1
 
+    # Multi-GPU gradient exchange: all-reduce + Adam + parameter all-gather fused into one kernel
+    # over NVLink peer memory (parallel.PeerAdam); --nccl-allreduce selects the baseline (NCCL
+    # all-reduce pipelined with the full local Adam pass), which is also the fallback when
+    # symmetric memory cannot be set up on this box.
+    peer, exchange = None, "none"
+    if world > 1:
+        exchange = "nccl-allreduce + local Adam"
+        if not args.nccl_allreduce:
+            try:
+                grp = next(g for g in pc.optimizer.param_groups
+                           if any(q is pc._semantic_feature for q in g["params"]))
+                peer = parallel.PeerAdam(pc._semantic_feature, lr=grp["lr"], betas=grp["betas"],
+                                         eps=grp["eps"])
+                exchange = "peer-memory fused all-reduce + sharded Adam + all-gather (one kernel)"
+            except Exception as e:                       # noqa: BLE001 - reported, NCCL path used
+                print(f"[bench] PeerAdam unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+                peer = None
+    if peer is not None:
+        R.direct_grad_accumulation = True
+
     def one_view(cam, target):
         pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
         if args.unfused_loss:
@@ -191,6 +216,9 @@ def main():
         return l1_backward_fused(pkg["render"], target[0], target[1])
 
     def opt_step():
+        if peer is not None:
+            peer.step()                                      # re-zeroes its persistent .grad itself
+            return
         if world > 1:
             parallel.allreduce_and_step(pc.optimizer, pc._semantic_feature, world)
         else:
@@ -348,6 +376,7 @@ def main():
                                        "(frozen geometry)",
                            "priming_steps": priming,
                            "views_per_step_per_gpu": kviews, "parallelism": f"view-dp{world}",
+                           "grad_exchange": exchange,
                            "l2": "inputs (2 GB feature table, 2 GB raster) exceed the 126 MB L2",
                            "optimizer_in_timed_region": True},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

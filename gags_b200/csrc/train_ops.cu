@@ -138,6 +138,54 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
   }
 }
 
+// ---- gradient all-reduce + Adam + parameter all-gather as ONE kernel over NVLink peer memory ---
+// View-parallel training replicates the feature table and sums its gradient over the ranks every
+// step (2 GB at config 3).  Here rank r owns the float4 range [start, start + count) of the table
+// (and only that slice of the Adam moments): it LOADS that range of every rank's gradient buffer
+// straight from peer memory, sums in rank order (every rank gets bit-identical parameters), applies
+// Adam, and STORES the new parameters into every rank's replica.  Inbound gradients and outbound
+// parameters use the two directions of the NVLink ports at the same time, the moments' HBM traffic
+// is divided by the world size, and no staging copy of the gradient exists.  The caller brackets
+// the launch with two inter-rank barriers (gradients final before; replicas complete after).
+constexpr int GAGS_MAX_PEERS = 16;
+struct PeerPtrs {
+  const float4 *grad[GAGS_MAX_PEERS];
+  float4 *param[GAGS_MAX_PEERS];
+};
+
+template <int MAXW>
+__global__ void __launch_bounds__(256)
+adam_peer_kernel(PeerPtrs pp, int world, int rank, float4 *__restrict__ m, float4 *__restrict__ v,
+                 long long start, long long count, float step_size, float b1, float b2, float omb1,
+                 float omb2, float inv_sqrt_bc2, float eps) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const long long i = start + k;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gq[MAXW];
+#pragma unroll
+    for (int q = 0; q < MAXW; ++q)
+      if (q < world) gq[q] = pp.grad[q][i];             // all loads in flight before the first add
+    float4 pa = pp.param[rank][i];
+    float4 ma = m[k], va = v[k];
+#pragma unroll
+    for (int q = 0; q < MAXW; ++q)
+      if (q < world) { g.x += gq[q].x; g.y += gq[q].y; g.z += gq[q].z; g.w += gq[q].w; }
+#define GAGS_ADAM1(P, G, M, V, c)                                 \
+    M.c = b1 * M.c + omb1 * G.c;                                  \
+    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
+    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
+    GAGS_ADAM1(pa, g, ma, va, x) GAGS_ADAM1(pa, g, ma, va, y)
+    GAGS_ADAM1(pa, g, ma, va, z) GAGS_ADAM1(pa, g, ma, va, w)
+#undef GAGS_ADAM1
+    m[k] = ma;
+    v[k] = va;
+#pragma unroll
+    for (int q = 0; q < MAXW; ++q)
+      if (q < world) pp.param[q][i] = pa;
+  }
+}
+
 __global__ void adam_tail_kernel(float *p, float *g, float *m, float *v, long long start,
                                  long long n, float step_size, float b1, float b2, float omb1,
                                  float omb2, float inv_sqrt_bc2, float eps, int zero_grad) {
@@ -248,6 +296,51 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
                                        (float)eps, zero_grad);
     GAGS_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
+                                   const uint64_t *param_ptrs, float *exp_avg_shard,
+                                   float *exp_avg_sq_shard, int64_t start, int64_t count, double lr,
+                                   double beta1, double beta2, double eps, int32_t step,
+                                   void *stream) {
+  if (!grad_ptrs || !param_ptrs || world < 1 || world > GAGS_MAX_PEERS || rank < 0 || rank >= world ||
+      start < 0 || count < 0 || step < 1)
+    return GAGS_EINVAL;
+  if (count == 0) return 0;
+  if (!exp_avg_shard || !exp_avg_sq_shard) return GAGS_EINVAL;
+  if ((start & 3) || (count & 3)) return GAGS_EALIGN;          // float4 granularity
+  if (!gags_aligned16(exp_avg_shard) || !gags_aligned16(exp_avg_sq_shard)) return GAGS_EALIGN;
+  PeerPtrs pp;
+  for (int q = 0; q < GAGS_MAX_PEERS; ++q) {
+    pp.grad[q] = nullptr;
+    pp.param[q] = nullptr;
+  }
+  for (int q = 0; q < world; ++q) {
+    if (!grad_ptrs[q] || !param_ptrs[q] || (grad_ptrs[q] & 15) || (param_ptrs[q] & 15))
+      return GAGS_EALIGN;
+    pp.grad[q] = reinterpret_cast<const float4 *>(grad_ptrs[q]);
+    pp.param[q] = reinterpret_cast<float4 *>(param_ptrs[q]);
+  }
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+  const long long c4 = count / 4;
+  long long blocks = (c4 + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;                  // NVLink latency: fill the SMs
+#define GAGS_PEER_LAUNCH(MAXW)                                                                   \
+  adam_peer_kernel<MAXW><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                      \
+      pp, world, rank, reinterpret_cast<float4 *>(exp_avg_shard),                                  \
+      reinterpret_cast<float4 *>(exp_avg_sq_shard), start / 4, c4, step_size, (float)beta1,        \
+      (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps)
+  if (world <= 2) GAGS_PEER_LAUNCH(2);
+  else if (world <= 4) GAGS_PEER_LAUNCH(4);
+  else if (world <= 8) GAGS_PEER_LAUNCH(8);
+  else GAGS_PEER_LAUNCH(16);
+#undef GAGS_PEER_LAUNCH
+  GAGS_CHECK_LAUNCH();
   return 0;
 }
 

@@ -90,3 +90,101 @@ def allreduce_and_step(optimizer, param: torch.Tensor, world: int, chunks: int =
         works[i].wait()            # orders the current stream behind that slice's reduction
 
     optimizer.step_chunks(param, ready)
+
+
+class PeerAdam:
+    """Gradient all-reduce + Adam + parameter all-gather as ONE kernel over NVLink peer memory
+    (`gags_adam_step_peer`, csrc/train_ops.cu) for the view-parallel loop: the baseline is
+    allreduce_and_step (NCCL all-reduce, then the full Adam pass on every rank).
+
+    The parameter and its gradient are moved into symmetric memory (every rank maps every rank's
+    buffers); rank r owns a contiguous 1/G slice of the table and of the Adam moments.  step():
+    barrier (all backward passes done) -> each rank pulls its slice of all G gradients over NVLink,
+    sums them in rank order, updates, and pushes the new parameters into all G replicas -> barrier.
+    Inbound gradients and outbound parameters use both directions of the links at once, the
+    moments' HBM traffic is divided by G, and every replica stays bit-identical.  The gradient
+    buffer is persistent: the backward reduces straight into it (rasterization's
+    direct_grad_accumulation) and it is re-zeroed on a second stream after the closing barrier.
+
+    Same arithmetic as FusedAdam on the summed gradient (the sum runs in rank order instead of
+    NCCL's tree order).  State is sharded: state_dict() holds this rank's slice only."""
+
+    def __init__(self, param: torch.Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _C
+        from . import rasterization as R
+        if not (param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()):
+            raise ValueError("PeerAdam needs a contiguous float32 CUDA parameter")
+        self._C, self._R = _C, R
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.param = param
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step_count = 0
+        dev = param.device
+        numel = param.numel()
+        pad = (-numel) % (4 * self.world)                 # equal float4-aligned slices
+        self.padded = numel + pad
+        self.per = self.padded // self.world
+        self.start = self.rank * self.per
+        # symmetric buffers: [0] parameters, [1] gradients
+        self._buf = symm_mem.empty(2 * self.padded, dtype=torch.float32, device=dev)
+        self._hdl = symm_mem.rendezvous(self._buf, self.group)
+        self._buf.zero_()
+        self._buf[:numel].copy_(param.detach().reshape(-1))
+        base = [int(p) for p in self._hdl.buffer_ptrs]
+        import ctypes
+        self._param_ptrs = (ctypes.c_uint64 * self.world)(*base)
+        self._grad_ptrs = (ctypes.c_uint64 * self.world)(*[b + 4 * self.padded for b in base])
+        # the module's parameter and its .grad now live in the symmetric buffer
+        param.data = self._buf[:numel].view(param.shape)
+        self.grad = self._buf[self.padded:self.padded + numel].view(param.shape)
+        param.grad = self.grad
+        self.exp_avg = torch.zeros(self.per, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.per, dtype=torch.float32, device=dev)
+        R.direct_grad_accumulation = True                 # the backward reduces into `.grad` in place
+        torch.cuda.synchronize(dev)
+        self._hdl.barrier()
+
+    @torch.no_grad()
+    def step(self) -> None:
+        C, R = self._C, self._R
+        p = self.param
+        if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr():
+            raise RuntimeError("PeerAdam: the parameter's .grad must stay the symmetric buffer "
+                               "(use zero_grad(), not set_to_none)")
+        self.step_count += 1
+        self._hdl.barrier()                               # every rank's backward has finished
+        C.check(C.lib.gags_adam_step_peer(self.world, self.rank, self._grad_ptrs, self._param_ptrs,
+                                          C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq), self.start,
+                                          self.per, self.lr, self.betas[0], self.betas[1], self.eps,
+                                          self.step_count, C.stream_ptr()), "gags_adam_step_peer")
+        C.count_launch()
+        self._hdl.barrier()                               # replicas complete, gradients consumed
+        self.zero_grad()
+
+    @torch.no_grad()
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Re-zero the persistent gradient buffer on the fill stream (beside the next view's
+        projection / sort); the next backward waits for it."""
+        C, R = self._C, self._R
+        dev = self.param.device
+        main = torch.cuda.current_stream(dev)
+        zs = R._zero_stream(dev)
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        zs.wait_event(ev0)
+        C.check(C.lib.gags_zero_fill(self._buf.data_ptr() + 4 * self.padded, 4 * self.padded,
+                                     zs.cuda_stream), "gags_zero_fill")
+        C.count_launch()
+        evz = torch.cuda.Event()
+        evz.record(zs)
+        R.sink_ready_events[self.grad.data_ptr()] = evz
+        self.param.grad = self.grad
+
+    def state_dict(self):
+        return {"step": self.step_count, "rank": self.rank, "world": self.world,
+                "exp_avg_shard": self.exp_avg, "exp_avg_sq_shard": self.exp_avg_sq,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}

@@ -461,6 +461,10 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
 # ------------------------------------------------------------------------------------------------
 # K7 / K8
 # ------------------------------------------------------------------------------------------------
+# data_ptr of a persistent `.grad` buffer -> event after which it is zeroed (parallel.PeerAdam)
+sink_ready_events: Dict = {}
+
+
 def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
     """The [N, D] buffer the feature backward accumulates into, and the leaf it belongs to when the
     reduction goes straight into `.grad` (direct_grad_accumulation)."""
@@ -469,6 +473,9 @@ def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
             and sink.grad.dtype == torch.float32:
         v_colors = sink.grad                     # accumulate in place: nothing to zero or add
         ctx.prezero = None
+        ev = sink_ready_events.pop(v_colors.data_ptr(), None)
+        if ev is not None:                       # a persistent buffer re-zeroed on another stream
+            torch.cuda.current_stream(dev).wait_event(ev)
     elif need_col and ctx.prezero is not None:
         v_colors, evz, _ = ctx.prezero
         cur = torch.cuda.current_stream(dev)

@@ -249,6 +249,19 @@ int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                    double lr, double beta1, double beta2, double eps, int32_t step,
                    int32_t zero_grad, void *stream);
 
+/* Multi-GPU form of gags_adam_step: gradient all-reduce + Adam + parameter all-gather in ONE kernel
+ * over NVLink peer memory (view-parallel training).  grad_ptrs[q] / param_ptrs[q]
+ * (host arrays of `world` device addresses, q = rank) are every rank's full [numel] gradient and
+ * parameter buffer, mapped into this process (CUDA IPC / symmetric memory).  This rank owns
+ * elements [start, start + count) (multiples of 4): it sums that range of all gradients in rank
+ * order, updates its slice of the moments (exp_avg_shard / exp_avg_sq_shard hold `count` floats)
+ * and writes the new parameters into every rank's buffer.  The caller provides an inter-rank
+ * barrier before (all gradients final) and after (all replicas written, gradients consumed).   */
+int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
+                        const uint64_t *param_ptrs, float *exp_avg_shard, float *exp_avg_sq_shard,
+                        int64_t start, int64_t count, double lr, double beta1, double beta2,
+                        double eps, int32_t step, void *stream);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);
