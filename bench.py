@@ -198,7 +198,8 @@ def main():
                            if any(q is pc._semantic_feature for q in g["params"]))
                 peer = parallel.PeerAdam(pc._semantic_feature, lr=grp["lr"], betas=grp["betas"],
                                          eps=grp["eps"])
-                exchange = "peer-memory fused all-reduce + sharded Adam + all-gather (one kernel)"
+                exchange = ("peer-memory fused all-reduce + sharded Adam + all-gather (one kernel, "
+                            + ("NVLS multimem" if peer.multicast else "unicast P2P") + ")")
             except Exception as e:                       # noqa: BLE001 - reported, NCCL path used
                 print(f"[bench] PeerAdam unavailable ({type(e).__name__}: {e}); using NCCL",
                       file=sys.stderr)
@@ -295,6 +296,9 @@ def main():
         e2e = {"value": steps_e * kviews * world / (ms_e * 1e-3), "unit": "views/s",
                "h2d_bytes_per_step": int(last[1]), "d2h_bytes_per_step": 4}
 
+    if peer is not None:
+        peer.synchronize()
+        torch.cuda.synchronize(dev)
     # ---- per-stage device times for the roofline (rank 0, single views, CUDA events) -------------
     stage_ms, stats, roofline = {}, {}, None
     if rank == 0:
@@ -355,6 +359,8 @@ def main():
         step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4) + H * W * (4 * D + 8) + n * (4 * D + 24)
         stats["step_hbm_frac_of_8TBps"] = step_bytes / (ms * 1e-3 / (args.steps * kviews)) / 8e12
         stats.update(alloc_stats)
+        if peer is not None and peer.timing_summary() is not None:
+            stats["peer_step_ms"] = peer.timing_summary()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -186,6 +186,57 @@ adam_peer_kernel(PeerPtrs pp, int world, int rank, float4 *__restrict__ m, float
   }
 }
 
+// The same step through the NVSwitch (NVLS): `mc_grad` / `mc_param` are MULTICAST addresses of the
+// symmetric buffers.  multimem.ld_reduce returns the sum over all ranks' copies, formed inside the
+// switch, and multimem.st writes all replicas with one store, so a rank moves 1/G of the table in
+// each direction instead of (G-1)/G and the kernel is bound by HBM, not by the NVLink ports.
+__global__ void __launch_bounds__(256)
+adam_multicast_kernel(const float4 *mc_grad, float4 *mc_param, const float4 *__restrict__ p_local,
+                      float4 *__restrict__ m, float4 *__restrict__ v, long long start,
+                      long long count, float step_size, float b1, float b2, float omb1, float omb2,
+                      float inv_sqrt_bc2, float eps) {
+  // a small grid (the exchange runs beside the next view's projection / sort) with four switch
+  // reductions in flight per thread to cover the NVLink round trip
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; k0 < count; k0 += U * stride) {
+    float4 g[U], pa[U], ma[U], va[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long k = k0 + u * stride;
+      if (k < count)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(g[u].x), "=f"(g[u].y), "=f"(g[u].z), "=f"(g[u].w)
+                     : "l"(mc_grad + start + k)
+                     : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long k = k0 + u * stride;
+      if (k < count) { pa[u] = p_local[start + k]; ma[u] = m[k]; va[u] = v[k]; }
+    }
+#define GAGS_ADAM1(P, G, M, V, c)                                 \
+    M.c = b1 * M.c + omb1 * G.c;                                  \
+    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
+    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long k = k0 + u * stride;
+      if (k < count) {
+        GAGS_ADAM1(pa[u], g[u], ma[u], va[u], x) GAGS_ADAM1(pa[u], g[u], ma[u], va[u], y)
+        GAGS_ADAM1(pa[u], g[u], ma[u], va[u], z) GAGS_ADAM1(pa[u], g[u], ma[u], va[u], w)
+        m[k] = ma[u];
+        v[k] = va[u];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(
+                         mc_param + start + k),
+                     "f"(pa[u].x), "f"(pa[u].y), "f"(pa[u].z), "f"(pa[u].w)
+                     : "memory");
+      }
+    }
+#undef GAGS_ADAM1
+  }
+}
+
 __global__ void adam_tail_kernel(float *p, float *g, float *m, float *v, long long start,
                                  long long n, float step_size, float b1, float b2, float omb1,
                                  float omb2, float inv_sqrt_bc2, float eps, int zero_grad) {
@@ -329,7 +380,7 @@ extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  if (blocks > 148LL * 8) blocks = 148LL * 8;                  // NVLink latency: fill the SMs
+  if (blocks > 148LL * 4) blocks = 148LL * 4;                  // half the thread slots stay free
 #define GAGS_PEER_LAUNCH(MAXW)                                                                   \
   adam_peer_kernel<MAXW><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                      \
       pp, world, rank, reinterpret_cast<float4 *>(exp_avg_shard),                                  \
@@ -340,6 +391,35 @@ extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *
   else if (world <= 8) GAGS_PEER_LAUNCH(8);
   else GAGS_PEER_LAUNCH(16);
 #undef GAGS_PEER_LAUNCH
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
+                                        const float *param_local, float *exp_avg_shard,
+                                        float *exp_avg_sq_shard, int64_t start, int64_t count,
+                                        double lr, double beta1, double beta2, double eps,
+                                        int32_t step, void *stream) {
+  if (!mc_grad || !mc_param || !param_local || start < 0 || count < 0 || step < 1) return GAGS_EINVAL;
+  if (count == 0) return 0;
+  if (!exp_avg_shard || !exp_avg_sq_shard) return GAGS_EINVAL;
+  if ((start & 3) || (count & 3)) return GAGS_EALIGN;
+  if (!gags_aligned16(mc_grad) || !gags_aligned16(mc_param) || !gags_aligned16(param_local) ||
+      !gags_aligned16(exp_avg_shard) || !gags_aligned16(exp_avg_sq_shard))
+    return GAGS_EALIGN;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+  const long long c4 = count / 4;
+  long long blocks = (c4 + 255) / 256;
+  if (blocks > 148LL * 2) blocks = 148LL * 2;                  // small grid, 4 reductions per thread
+  adam_multicast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),
+      reinterpret_cast<const float4 *>(param_local), reinterpret_cast<float4 *>(exp_avg_shard),
+      reinterpret_cast<float4 *>(exp_avg_sq_shard), start / 4, c4, step_size, (float)beta1,
+      (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps);
   GAGS_CHECK_LAUNCH();
   return 0;
 }

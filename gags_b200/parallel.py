@@ -123,6 +123,7 @@ class PeerAdam:
         self.param = param
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.step_count = 0
+        self.timing = [] if os.environ.get("GAGS_B200_PEER_TIMING") else None   # per-step CUDA events
         dev = param.device
         numel = param.numel()
         pad = (-numel) % (4 * self.world)                 # equal float4-aligned slices
@@ -142,6 +143,16 @@ class PeerAdam:
         param.data = self._buf[:numel].view(param.shape)
         self.grad = self._buf[self.padded:self.padded + numel].view(param.shape)
         param.grad = self.grad
+        # NVLS: with multicast addresses the switch forms the gradient sum (multimem.ld_reduce) and
+        # replicates the parameter stores (multimem.st): per direction a rank then moves 2 GB + 2 GB/G
+        # instead of 2 * (G-1)/G * 2 GB — a gain from G > 4 on (GAGS_B200_NVLS=0/1 overrides).
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        want = os.environ.get("GAGS_B200_NVLS", "auto")
+        self.multicast = mc != 0 and (want == "1" or (want == "auto" and self.world > 4))
+        self._mc_param = mc
+        self._mc_grad = mc + 4 * self.padded
+        self._xstream = torch.cuda.Stream(device=dev, priority=-1)
+        self._done = None
         self.exp_avg = torch.zeros(self.per, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.per, dtype=torch.float32, device=dev)
         R.direct_grad_accumulation = True                 # the backward reduces into `.grad` in place
@@ -150,39 +161,82 @@ class PeerAdam:
 
     @torch.no_grad()
     def step(self) -> None:
+        """Enqueue the exchange on its own stream behind everything the current stream has queued
+        (the backward).  The current stream is free to run the next view's projection / tile sort
+        meanwhile — they read no feature — and the next forward blend waits for the new parameters
+        (rasterization.param_ready_events); call synchronize() before reading the parameter any
+        other way."""
         C, R = self._C, self._R
         p = self.param
         if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr():
             raise RuntimeError("PeerAdam: the parameter's .grad must stay the symmetric buffer "
                                "(use zero_grad(), not set_to_none)")
         self.step_count += 1
-        self._hdl.barrier()                               # every rank's backward has finished
-        C.check(C.lib.gags_adam_step_peer(self.world, self.rank, self._grad_ptrs, self._param_ptrs,
-                                          C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq), self.start,
-                                          self.per, self.lr, self.betas[0], self.betas[1], self.eps,
-                                          self.step_count, C.stream_ptr()), "gags_adam_step_peer")
-        C.count_launch()
-        self._hdl.barrier()                               # replicas complete, gradients consumed
-        self.zero_grad()
+        dev = p.device
+        main = torch.cuda.current_stream(dev)
+        xs = self._xstream
+        ev_b = torch.cuda.Event()
+        ev_b.record(main)
+        xs.wait_event(ev_b)
+        with torch.cuda.stream(xs):
+            ev = None
+            if self.timing is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record(xs)
+            self._hdl.barrier()                           # every rank's backward has finished
+            if ev:
+                ev[1].record(xs)
+            if self.multicast:
+                C.check(C.lib.gags_adam_step_multicast(
+                    self._mc_grad, self._mc_param, self._buf.data_ptr(), C.ptr(self.exp_avg),
+                    C.ptr(self.exp_avg_sq), self.start, self.per, self.lr, self.betas[0],
+                    self.betas[1], self.eps, self.step_count, xs.cuda_stream),
+                    "gags_adam_step_multicast")
+            else:
+                C.check(C.lib.gags_adam_step_peer(
+                    self.world, self.rank, self._grad_ptrs, self._param_ptrs, C.ptr(self.exp_avg),
+                    C.ptr(self.exp_avg_sq), self.start, self.per, self.lr, self.betas[0],
+                    self.betas[1], self.eps, self.step_count, xs.cuda_stream),
+                    "gags_adam_step_peer")
+            C.count_launch()
+            if ev:
+                ev[2].record(xs)
+            self._hdl.barrier()                           # replicas complete, gradients consumed
+            if ev:
+                ev[3].record(xs)
+                self.timing.append(ev)
+            # re-zero the persistent gradient buffer for the next backward
+            C.check(C.lib.gags_zero_fill(self._buf.data_ptr() + 4 * self.padded, 4 * self.padded,
+                                         xs.cuda_stream), "gags_zero_fill")
+            C.count_launch()
+            done = torch.cuda.Event()
+            done.record(xs)
+        self._done = done
+        R.param_ready_events[p.data_ptr()] = done         # the next forward blend waits for this
+        R.sink_ready_events[self.grad.data_ptr()] = done  # ... and so does the next backward
+        p.grad = self.grad
+
+    def synchronize(self) -> None:
+        """Order the current stream behind the last exchange (before reading the parameter)."""
+        if self._done is not None:
+            torch.cuda.current_stream(self.param.device).wait_event(self._done)
 
     @torch.no_grad()
     def zero_grad(self, set_to_none: bool = False) -> None:
-        """Re-zero the persistent gradient buffer on the fill stream (beside the next view's
-        projection / sort); the next backward waits for it."""
-        C, R = self._C, self._R
-        dev = self.param.device
-        main = torch.cuda.current_stream(dev)
-        zs = R._zero_stream(dev)
-        ev0 = torch.cuda.Event()
-        ev0.record(main)
-        zs.wait_event(ev0)
-        C.check(C.lib.gags_zero_fill(self._buf.data_ptr() + 4 * self.padded, 4 * self.padded,
-                                     zs.cuda_stream), "gags_zero_fill")
-        C.count_launch()
-        evz = torch.cuda.Event()
-        evz.record(zs)
-        R.sink_ready_events[self.grad.data_ptr()] = evz
+        """step() already re-zeroes the persistent buffer; kept for optimiser-API symmetry."""
         self.param.grad = self.grad
+
+    def timing_summary(self, last: int = 10):
+        """Average ms of (wait for the slowest rank, fused kernel, closing barrier) over the last
+        steps; needs GAGS_B200_PEER_TIMING=1."""
+        if not self.timing:
+            return None
+        torch.cuda.synchronize(self.param.device)
+        ev = self.timing[-last:]
+        n = len(ev)
+        return {"barrier_in_ms": sum(e[0].elapsed_time(e[1]) for e in ev) / n,
+                "kernel_ms": sum(e[1].elapsed_time(e[2]) for e in ev) / n,
+                "barrier_out_ms": sum(e[2].elapsed_time(e[3]) for e in ev) / n}
 
     def state_dict(self):
         return {"step": self.step_count, "rank": self.rank, "world": self.world,

@@ -463,6 +463,9 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
 # ------------------------------------------------------------------------------------------------
 # data_ptr of a persistent `.grad` buffer -> event after which it is zeroed (parallel.PeerAdam)
 sink_ready_events: Dict = {}
+# data_ptr of a feature table -> event after which its latest optimiser update has landed (PeerAdam
+# runs the multi-GPU exchange on its own stream, beside the next view's projection / sort)
+param_ready_events: Dict = {}
 
 
 def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
@@ -571,6 +574,10 @@ class _Blend(torch.autograd.Function):
         colors = _f32c(colors)
         N, D = colors.shape
         dev = colors.device
+        if param_ready_events:
+            ev = param_ready_events.pop(colors.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
         if D > 32 and D % 4 != 0:
             raise ValueError("wide blend needs D % 4 == 0 (rasterization() pads for you)")
         bg = _f32c(background) if background is not None else None

@@ -262,6 +262,16 @@ int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
                         int64_t start, int64_t count, double lr, double beta1, double beta2,
                         double eps, int32_t step, void *stream);
 
+/* gags_adam_step_peer through the NVSwitch: mc_grad / mc_param are the MULTICAST addresses of the
+ * symmetric gradient / parameter buffers (NVLS).  The gradient sum is formed inside the switch
+ * (multimem.ld_reduce) and one multimem.st updates every replica, so each rank moves 1/world of
+ * the table per direction.  param_local = this rank's own (unicast) parameter buffer.  Same
+ * barriers around the call as gags_adam_step_peer.                                              */
+int gags_adam_step_multicast(const float *mc_grad, float *mc_param, const float *param_local,
+                             float *exp_avg_shard, float *exp_avg_sq_shard, int64_t start,
+                             int64_t count, double lr, double beta1, double beta2, double eps,
+                             int32_t step, void *stream);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);

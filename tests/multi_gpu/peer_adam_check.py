@@ -35,6 +35,7 @@ for step in range(3):
         torch.cuda.current_stream().wait_event(ev)
     par.grad.add_(grad)
     peer.step()
+    peer.synchronize()
 torch.cuda.synchronize()
 err = float((par.detach() - ref.detach()).abs().max() / ref.detach().abs().max())
 # replicas identical across ranks
@@ -43,7 +44,7 @@ allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 same = all(float(c) == float(allc[0]) for c in allc)
 ok = err < 1e-6 and same
-print(f"rank {rank}: rel err vs all_reduce + FusedAdam {err:.3e}, replicas identical {same} -> "
+print(f"rank {rank}: multicast={peer.multicast} rel err vs all_reduce + FusedAdam {err:.3e}, replicas identical {same} -> "
       f"{'OK' if ok else 'FAIL'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
