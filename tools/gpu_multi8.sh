@@ -7,6 +7,7 @@ export GAGS_B200_PEER_TIMING=1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
 for MODE in ${MODES:-auto unicast}; do
   [ "$MODE" = "unicast" ] && export GAGS_B200_NVLS=0
+  [ "$MODE" = "nvls" ] && export GAGS_B200_NVLS=1
   timeout 400 $TR --master-port 29517 bench.py --gpus $NG --steps ${STEPS:-10} --warmup 3 \
     --no-cpu-baseline > gpurun_out/bench_${NG}gpu_$MODE.log 2> gpurun_out/bench_${NG}gpu_$MODE.err
   echo "$MODE rc=$?"; tail -1 gpurun_out/bench_${NG}gpu_$MODE.log | python -c "
