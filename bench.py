@@ -7,8 +7,10 @@
 
 One step = one optimiser step of the train.py loop (/root/reference/train.py:109-228) with frozen
 geometry on the config-3 shape (N=2M Gaussians, 1080x1920, D=256): for each of `views_per_step`
-views per rank  render() -> fused L1 against a fixed random target -> backward to the per-Gaussian
-features;  then (N>1) NCCL all-reduce of the feature gradient;  then Adam on the feature table.
+views per rank (default 1 at every N)  render() -> L1 against the view's emb[seg] target fused with
+the backward to the per-Gaussian features (l1_backward_fused);  then Adam on the feature table —
+at N>1 fused with the gradient all-reduce and the parameter all-gather into one NVLink peer-memory
+kernel (parallel.PeerAdam; --nccl-allreduce = NCCL all-reduce + local Adam, also the fallback).
 value = views/sec over the whole job (all ranks), inputs resident in HBM.
 e2e   = the same loop with the per-view training target (segment map + embedding table, the
         inputs of the reference's read_sam_clip_feature) copied from pinned host memory each view

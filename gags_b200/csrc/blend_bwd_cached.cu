@@ -184,26 +184,34 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
       const float *vbase = v_render + jb.cfirst + n0;
       // pixels per round: the fused-loss form also holds the target rows, so it takes half as many
       constexpr int PJ = L1 ? 4 : 8;
+      int sg_cur[PJ];
+      auto load_seg = [&](int round) {
+#pragma unroll
+        for (int jj = 0; jj < PJ; ++jj) {
+          const int ql = 2 * (round * PJ + jj) + (lane >> 4);
+          const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+          sg_cur[jj] = -1;
+          if (L1 && chan_ok && xx < W && yy < H) sg_cur[jj] = __ldg(l1.seg + (size_t)yy * W + xx);
+        }
+      };
+      if constexpr (L1) load_seg(0);
       // first half of the loads may fly before the previous job's MMAs have released the buffer
 #pragma unroll 1
       for (int round = 0; round < 16 / PJ; ++round) {
         float4 v[PJ][2];
         if constexpr (L1) {
-          // segment id (and mask) first: the target row's address depends on it
+          // the segment ids of this round were loaded one round ahead (sg_cur): the target row's
+          // address depends on them, and a load chain seg -> emb per round showed up as +0.1 ms
           int sg[PJ];
           float mk[PJ];
 #pragma unroll
           for (int jj = 0; jj < PJ; ++jj) {
             const int ql = 2 * (round * PJ + jj) + (lane >> 4);
             const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
-            sg[jj] = -1;
-            mk[jj] = 1.f;
-            if (chan_ok && xx < W && yy < H) {
-              sg[jj] = __ldg(l1.seg + (size_t)yy * W + xx);
-              if (l1.mask) mk[jj] = fabsf(__ldg(l1.mask + (size_t)yy * W + xx));
-            } else {
-              mk[jj] = 0.f;
-            }
+            sg[jj] = sg_cur[jj];
+            mk[jj] = 0.f;
+            if (chan_ok && xx < W && yy < H)
+              mk[jj] = l1.mask ? fabsf(__ldg(l1.mask + (size_t)yy * W + xx)) : 1.f;
           }
           float4 t[PJ][2];
 #pragma unroll
@@ -225,6 +233,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
               }
             }
           }
+          if (round + 1 < 16 / PJ) load_seg(round + 1);
 #pragma unroll
           for (int jj = 0; jj < PJ; ++jj) {
             const float sc = l1.scale * mk[jj];
