@@ -698,3 +698,58 @@ def test_fused_l1_backward_falls_back_without_cache():
             l1_loss_segmap_fused(pkg["render"], seg, emb).backward()
         grads.append(pc._semantic_feature.grad.clone())
     assert rel_err(grads[1], grads[0]) < 2e-6
+
+
+def test_fused_l1_backward_through_nonleaf_features_and_oracle():
+    """the features reach the blend through an autograd op (a non-leaf): the fused call hands its
+    gradient to autograd instead of adopting it as .grad; loss and gradient are also checked
+    against the fp64 oracle's render with torch's own |x| backward."""
+    from gags_b200 import rasterization as R
+    from gags_b200.utils.loss_utils import l1_backward_fused
+    W, H, D = 96, 64, 64
+    sc = front_scene(900, W, H, D, seed=31)
+    g = _cuda(sc)
+    K = sc["K"]
+    gen = torch.Generator().manual_seed(2)
+    S = 7
+    seg = torch.randint(-1, S, (H, W), generator=gen, dtype=torch.int32)
+    emb = 0.3 * torch.randn(S, D, generator=gen)
+    leaf = torch.nn.Parameter(g["colors"].clone())
+    cols = leaf * 2.0                                         # non-leaf input of the blend
+    render, _, _ = R.rasterize_view(g["means"], g["quats"], g["scales"], g["opacities"], cols,
+                                    g["viewmat"], float(K[0, 0]), float(K[1, 1]), float(K[0, 2]),
+                                    float(K[1, 2]), W, H, background=torch.zeros(D, device="cuda"))
+    rd = render.permute(2, 0, 1)
+    rd._gags_fused = render._gags_fused
+    loss = l1_backward_fused(rd, seg.cuda(), emb.cuda())
+    torch.cuda.synchronize()
+    # oracle
+    d = {k: v.double() for k, v in sc.items() if torch.is_tensor(v)}
+    leaf64 = d["colors"].clone().requires_grad_(True)
+    ref, _, _ = O.rasterization(d["means"], d["quats"], d["scales"], d["opacities"], leaf64 * 2.0,
+                                d["viewmat"], d["K"], W, H, torch.zeros(D, dtype=torch.float64))
+    ok = (seg >= 0)
+    tgt = emb.double()[seg.clamp(min=0).long()]
+    ref_loss = ((ref - tgt).abs() * ok[..., None]).sum() / (H * W * D)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    # sign() flips where the render is within rounding of the target: compare by fraction
+    assert frac_bad(leaf.grad, leaf64.grad, 2e-3) < 5e-3
+
+
+def test_zero_fill_and_guarded_sort_argument_checks():
+    from gags_b200 import _C
+    x = torch.randn(100_003 * 4, device="cuda")
+    _C.check(_C.lib.gags_zero_fill(x.data_ptr(), x.numel() * 4, _C.stream_ptr()))
+    torch.cuda.synchronize()
+    assert float(x.abs().max()) == 0.0
+    y = torch.ones(64, device="cuda")
+    assert _C.lib.gags_zero_fill(y.data_ptr() + 4, 32, _C.stream_ptr()) != 0      # misaligned
+    assert _C.lib.gags_zero_fill(y.data_ptr(), 20, _C.stream_ptr()) != 0          # not 16-B multiple
+    assert _C.lib.gags_zero_fill(y.data_ptr(), 0, _C.stream_ptr()) == 0
+    torch.cuda.synchronize()
+    assert float(y.min()) == 1.0
+    assert _C.lib.gags_tile_bucket_sort_guarded(None, 4, 4, None, 10, None, None,
+                                                _C.stream_ptr()) != 0
+    assert _C.lib.gags_adam_step_peer(0, 0, None, None, None, None, 0, 0, 1e-3, 0.9, 0.999, 1e-8,
+                                      1, _C.stream_ptr()) != 0
