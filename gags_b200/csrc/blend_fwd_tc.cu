@@ -4,7 +4,9 @@
 //
 // The D-wide blend of one 16x8 half tile is the dense product
 //        render[128 px, D] = Wt[128 px, G] * F[G, D],      Wt[p, g] = alpha_g(p) * T_g(p)
-// over the tile's depth-sorted Gaussians.  fp32 parity (1e-4) is kept on bf16 tensor cores by
+// over the tile's depth-sorted Gaussians; it is issued transposed, acc[D, 128 px] = F^T * Wt^T
+// (feature tile = MN-major A operand, 128 channels per instruction; weight tile = K-major B operand,
+// N = 128 pixels), so that a TMEM lane is a channel and the epilogue needs no transpose.  fp32 parity (1e-4) is kept on bf16 tensor cores by
 // splitting both operands x = hi + lo (bf16 each, |x - hi - lo| <= 2^-18 |x|) and issuing three
 // products hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (measured 4e-6 relative,
 // tools/umma_probe.cu).
@@ -21,10 +23,10 @@
 //               [hi(32) | lo(32)] (128 B, K-major SWIZZLE_128B).
 //   warp 13     (training) one thread stores each blended batch's weight tile to the cache with a
 //               bulk async copy for the cached backward (blend_bwd_cached.cu).
-//   warp 12     one thread issues tcgen05.mma (M=128, N=D, K=16) x 3 products x 2 k-steps per batch;
-//               tcgen05.commit frees the stage.
-// Epilogue (warps 0-11): tcgen05.ld -> + T*background -> per-warp transpose in smem -> 128-B
-// coalesced streaming stores of the channel-last raster.
+//   warp 12     one thread issues tcgen05.mma (M=128 channels, N=128 pixels, K=16) x ceil(D/128)
+//               channel blocks x 3 products x 2 k-steps per batch; tcgen05.commit frees the stage.
+// Epilogue (warps 0-11): tcgen05.ld (lane = channel, column = pixel) -> + T*background (skipped
+// for an all-zero background) -> 128-B warp-wide streaming stores of the channel-last raster.
 //
 // Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
 // hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
@@ -73,8 +75,7 @@ struct TcLayout {
   static constexpr int A_OFF = 0;                      // 2 stages x 16 KB
   static constexpr int B_OFF = 32768;                  // [stage][part][BPART]
   static constexpr int RING_OFF = B_OFF + 4 * BPART;
-  static constexpr int STG_END = 12 * 4096;            // epilogue staging: 12 warps x 4 KB from 0
-  static constexpr int CTL_OFF = (RING_OFF + RING * 36) > STG_END ? (RING_OFF + RING * 36) : STG_END;
+  static constexpr int CTL_OFF = RING_OFF + RING * 36;
   static constexpr int BYTES = CTL_OFF + (int)sizeof(TcCtl) + 1024;   // + alignment slack
   static constexpr int MB = (NATOM + 1) / 2;           // 128-channel blocks (MMA M)
   static constexpr int TCOLS = MB * 128;               // accumulator: lane = channel, column = pixel

@@ -624,7 +624,8 @@ def test_gsplat_shaped_entry_point():
 
 @pytest.mark.parametrize("H,W,D,with_mask,direct", [(96, 160, 64, False, False),
                                                     (75, 131, 256, True, False),
-                                                    (64, 96, 128, False, True)])
+                                                    (64, 96, 128, False, True),
+                                                    (40, 56, 512, True, False)])
 def test_fused_l1_backward_equals_loss_then_backward(H, W, D, with_mask, direct):
     """fused_l1_backward (loss gradient formed inside the cached backward) == l1_loss_segmap_fused +
     loss.backward(): same loss, same feature gradient — pixels without a target (seg < 0), a mask,
