@@ -209,8 +209,10 @@ def main():
     if peer is not None:
         R.direct_grad_accumulation = True
 
-    def one_view(cam, target):
+    def one_view(cam, target, target_ready=None):
         pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
+        if target_ready is not None:                         # the target's H2D copy (copy stream)
+            torch.cuda.current_stream(dev).wait_event(target_ready)
         if args.unfused_loss:
             loss = l1_loss_segmap_fused(pkg["render"], target[0], target[1])
             loss.backward()
@@ -235,15 +237,24 @@ def main():
         opt_step()
         return loss
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def step_e2e(step):
         loss = None
         h2d = 0
         for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
             cam = cams[v]                 # cameras live on the device (scene/cameras.py:58)
-            seg = seg_host[v % n_targets].to(dev, non_blocking=True)
-            emb = emb_host[v % n_targets].to(dev, non_blocking=True)
+            # this view's target travels on a copy stream while the view renders; the loss waits
+            with torch.cuda.stream(copy_stream):
+                seg = seg_host[v % n_targets].to(dev, non_blocking=True)
+                emb = emb_host[v % n_targets].to(dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            main = torch.cuda.current_stream(dev)
+            seg.record_stream(main)
+            emb.record_stream(main)
             h2d += seg.numel() * 4 + emb.numel() * 4
-            loss = one_view(cam, (seg, emb))
+            loss = one_view(cam, (seg, emb), ready)
         opt_step()
         return float(loss.item()), h2d                       # D2H read of the step's loss
 
