@@ -92,6 +92,15 @@ def allreduce_and_step(optimizer, param: torch.Tensor, world: int, chunks: int =
     optimizer.step_chunks(param, ready)
 
 
+def peer_slices(numel: int, world: int) -> tuple[int, int]:
+    """(padded element count, elements per rank) of PeerAdam's ownership split: equal contiguous
+    slices, each a whole number of float4s, covering `numel`."""
+    if numel < 0 or world < 1:
+        raise ValueError("numel >= 0 and world >= 1")
+    padded = numel + (-numel) % (4 * world)
+    return padded, padded // world
+
+
 class PeerAdam:
     """Gradient all-reduce + Adam + parameter all-gather as ONE kernel over NVLink peer memory
     (`gags_adam_step_peer`, csrc/train_ops.cu) for the view-parallel loop: the baseline is
@@ -126,9 +135,7 @@ class PeerAdam:
         self.timing = [] if os.environ.get("GAGS_B200_PEER_TIMING") else None   # per-step CUDA events
         dev = param.device
         numel = param.numel()
-        pad = (-numel) % (4 * self.world)                 # equal float4-aligned slices
-        self.padded = numel + pad
-        self.per = self.padded // self.world
+        self.padded, self.per = peer_slices(numel, self.world)
         self.start = self.rank * self.per
         # symmetric buffers: [0] parameters, [1] gradients
         self._buf = symm_mem.empty(2 * self.padded, dtype=torch.float32, device=dev)

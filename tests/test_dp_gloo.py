@@ -81,3 +81,33 @@ def test_allreduce_equals_single_process_sum(tmp_path):
     # pipelined all-reduce + step: every slice reduced before it was consumed
     assert res["seen"] == [0, 1, 2, 3]
     assert torch.allclose(res["q"], -expect, atol=1e-6)
+
+
+def test_peer_slices_cover_the_table_in_float4_units():
+    """ownership split of parallel.PeerAdam: equal, 16-byte aligned, contiguous, complete."""
+    from gags_b200.parallel import peer_slices
+    for numel in (0, 1, 7, 640448, 2_000_000 * 256, 10007 * 64):
+        for world in (1, 2, 3, 4, 8, 16):
+            padded, per = peer_slices(numel, world)
+            assert per * world == padded >= numel and padded - numel < 4 * world
+            assert per % 4 == 0
+            starts = [r * per for r in range(world)]
+            assert all(s % 4 == 0 for s in starts)
+            assert starts[-1] + per == padded
+    import pytest
+    with pytest.raises(ValueError):
+        peer_slices(10, 0)
+
+
+def test_views_for_rank_one_view_per_rank_is_a_partition():
+    """bench.py's default at every N: step s, rank r renders view (s*G + r) mod n_views."""
+    from gags_b200.parallel import views_for_rank
+    n_views = 64
+    for world in (1, 2, 4, 8):
+        seen = []
+        for step in range(n_views // world):
+            for r in range(world):
+                v = views_for_rank(step, r, world, 1, n_views)
+                assert v == [(step * world + r) % n_views]
+                seen += v
+        assert sorted(seen) == list(range(n_views))
