@@ -279,6 +279,8 @@ def main():
             last = fn(warmup + i)
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
+        if peer is not None:
+            peer.synchronize()        # the last step's exchange runs on its own stream: drain it
         e1.record()
         barrier()
         sampler.stop_flag = True
