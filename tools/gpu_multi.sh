@@ -1,6 +1,6 @@
 #!/bin/bash
-# Multi-GPU visit: PeerAdam check + bench.py under torchrun at $NG ranks (fused peer step and, with
-# NCCL=1, the NCCL all-reduce baseline).
+# Multi-GPU visit: PeerAdam check (unicast and NVLS forms) + bench.py under torchrun at $NG ranks.
+# MODES: peer (default exchange), nvls (force multimem), nccl (NCCL all-reduce + local Adam baseline).
 NG=${NG:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
