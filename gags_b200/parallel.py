@@ -1,7 +1,9 @@
 """View-parallel data parallelism.  The reference has no multi-GPU code; the path
 shards naturally by training view: one process per GPU, a full replica of the Gaussians on each,
 rank r renders views {step*G*k + r*k ... + k-1}, and the only exchange is a sum of
-`_semantic_feature.grad` [N,D] over ranks before the (identical) local Adam step."""
+`_semantic_feature.grad` [N,D] over ranks before the Adam step — as an NCCL all-reduce followed by
+the identical local step (allreduce_grads / allreduce_and_step), or fused with the step and the
+parameter redistribution into one NVLink peer-memory kernel (PeerAdam)."""
 from __future__ import annotations
 
 import os
