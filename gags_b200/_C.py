@@ -77,6 +77,7 @@ SIGNATURES = {
     "gags_zero_fill": (C.c_int, [_p, _i64, _p]),
     "gags_adam_step_multicast": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, C.c_double, C.c_double,
                                            C.c_double, C.c_double, _i32, _p]),
+    "gags_set_peer_grid": (C.c_int, [_i32]),
     "gags_adam_step_peer": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _i64, C.c_double,
                                       C.c_double, C.c_double, C.c_double, _i32, _p]),
     "gags_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double,

@@ -350,6 +350,15 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   return 0;
 }
 
+// Tuning hook for the two exchange kernels (tools/peer_rate.py sweeps it): CTAs per SM of their
+// grids; 0 = the built-in choice (4 for the unicast form, 2 for the multicast form).
+static int g_peer_ctas_per_sm = 0;
+extern "C" int gags_set_peer_grid(int32_t ctas_per_sm) {
+  if (ctas_per_sm < 0 || ctas_per_sm > 16) return GAGS_EINVAL;
+  g_peer_ctas_per_sm = ctas_per_sm;
+  return 0;
+}
+
 extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
                                    const uint64_t *param_ptrs, float *exp_avg_shard,
                                    float *exp_avg_sq_shard, int64_t start, int64_t count, double lr,
@@ -380,7 +389,8 @@ extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  if (blocks > 148LL * 4) blocks = 148LL * 4;                  // half the thread slots stay free
+  const long long cap_u = 148LL * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 4);
+  if (blocks > cap_u) blocks = cap_u;                          // default: half the thread slots free
 #define GAGS_PEER_LAUNCH(MAXW)                                                                   \
   adam_peer_kernel<MAXW><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                      \
       pp, world, rank, reinterpret_cast<float4 *>(exp_avg_shard),                                  \
@@ -414,7 +424,8 @@ extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  if (blocks > 148LL * 2) blocks = 148LL * 2;                  // small grid, 4 reductions per thread
+  const long long cap_m = 148LL * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
+  if (blocks > cap_m) blocks = cap_m;                          // small grid, 4 reductions per thread
   adam_multicast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),
       reinterpret_cast<const float4 *>(param_local), reinterpret_cast<float4 *>(exp_avg_shard),

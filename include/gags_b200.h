@@ -272,6 +272,10 @@ int gags_adam_step_multicast(const float *mc_grad, float *mc_param, const float 
                              int64_t count, double lr, double beta1, double beta2, double eps,
                              int32_t step, void *stream);
 
+/* Tuning hook: CTAs per SM of the two exchange kernels' grids (0 = built-in: 4 unicast, 2
+ * multicast).  Process-wide; used by tools/peer_rate.py.                                         */
+int gags_set_peer_grid(int32_t ctas_per_sm);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);
