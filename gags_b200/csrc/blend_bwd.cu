@@ -454,12 +454,10 @@ int launch_bwd_feat_wide(const float *geom, int D, int ch0, int W, int H, const 
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + HROWS - 1) / HROWS;
   const size_t smem = sizeof(BwdSmem<NJ>);
-  static bool attr_done = false;
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (a process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(blend_bwd_feat_wide<NJ>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   blend_bwd_feat_wide<NJ><<<dim3(tw, hh), 256, smem, st>>>(reinterpret_cast<const float4 *>(geom), D,
                                                           ch0, W, H, tw, offsets, ids, v_render,

@@ -420,16 +420,14 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
   const int nblk = (nch + 127) / 128;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (a process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<L1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   const long long njobs = (long long)tw * nblk * hh;
   if (njobs > 0x7fffffffLL - 4096) return GAGS_ERANGE;
-  const long long want = 2LL * 148;                  // two persistent CTAs per SM
+  const long long want = 2LL * gags_sm_count();                  // two persistent CTAs per SM
   const unsigned grid = (unsigned)(njobs < want ? njobs : want);
   int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
   cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);

@@ -361,12 +361,10 @@ int launch_bw(const float *geom, int D, int ch0, int nch, int W, int H, const in
   using L = BwLayout<MB>;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (a process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(blend_bwd_tc<MB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   blend_bwd_tc<MB><<<dim3(tw, hh), BW_THREADS, L::BYTES, st>>>(
       reinterpret_cast<const float4 *>(geom), D, ch0, nch, W, H, tw, offsets, ids, v_render,

@@ -298,12 +298,10 @@ int launch_wide(const float *geom, const float *colors, int D, int ch0, const fl
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + HROWS - 1) / HROWS;
   const size_t smem = sizeof(WideSmem<NJ>);
-  static bool attr_done = false;
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (a process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(blend_fwd_wide<NJ>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   blend_fwd_wide<NJ><<<dim3(tw, hh), 256, smem, st>>>(reinterpret_cast<const float4 *>(geom), colors,
                                                      D, ch0, bg, W, H, tw, offsets, ids, render,

@@ -63,6 +63,11 @@ struct TcCtl {
   int done_warps, skip_from, any_mma;
   int wcnt[4];
   int gid[2][KB];
+  // v3 roles (front = scanner + alpha evaluation, chain = transmittance chain)
+  uint64_t alpha[2][4];               // front warp w -> chain warp w: alpha rows of block w written
+  int lidx[2][4][KB];                 // list index of each batch entry (for last_ids), per front warp
+  int nbw[2][4];                      // batch size as published by front warp w (== gcount)
+  int wdone[4];                       // chain warp w: all 32 pixels finished
   alignas(16) float Tfin[128];
   alignas(16) float bgs[256];
   alignas(16) float4 rec0[2][KB];     // per-stage batch records read by the pixel threads
@@ -83,7 +88,7 @@ struct TcLayout {
 // two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
 static_assert(TcLayout<4>::BYTES <= (233472 / 2 - 1024), "forward TC kernel must fit twice per SM");
 
-template <int NATOM>
+template <int NATOM, bool V3>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, int D, int ch0,
              int nch, const float *__restrict__ bg, int W, int H, int tile_w,
@@ -128,7 +133,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       mbar_init(&ctl.sdone[k], 1);                 // training: the tile store has read the A stage
       mbar_init(&ctl.afull[k], 4);                 // training: pixel warps -> store warp, A tile written
       ctl.gcount[k] = 0; ctl.skip[k] = 0;
+      for (int w = 0; w < 4; ++w) mbar_init(&ctl.alpha[k][w], 1);
     }
+    for (int w = 0; w < 4; ++w) ctl.wdone[w] = 0;
     ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0; ctl.term = -1;
     mbar_fence_init();
   }
@@ -146,7 +153,139 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   tc_fence_after();
   const uint32_t tb = ctl.tmem_base;
 
-  if (warp < 4) {
+  if (V3 && warp < 4) {
+    // ======================= v3 chain warps: one thread per pixel ==================================
+    // reads the 32 alphas the front warp of the same 8x4 block left in this pixel's A-tile row,
+    // runs the transmittance chain and overwrites the row with the bf16 [hi | lo] weights
+    const int pw = warp;
+    const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
+    const int pxi = x0 + dx, pyi = y0 + dy;
+    const bool inside = (pxi < W) && (pyi < H);
+    TcChain ps;
+    ps.P = inside ? 1.f : 0.f; ps.T = 1.f; ps.last = 0;
+    bool counted = false;
+    const uint32_t rowoff = (uint32_t)tid * 128u;
+    int i = 0;
+    for (;; ++i) {
+      const int st = i & 1;
+      if (warp == 0) TC_STAMP(0, i, 0);
+      mbar_wait_bounded(&ctl.alpha[st][pw], (i >> 1) & 1);
+      if (warp == 0) TC_STAMP(0, i, 1);
+      const int nb = *reinterpret_cast<volatile int *>(&ctl.nbw[st][pw]);
+      if (nb == 0) {
+        // batch i does not exist: tell the store warp (the front warps have already seen the store
+        // of batch i-2 before publishing, so the store warp is never two phases behind `afull`)
+        if (cache) {
+          if (warp == 0 && lane == 0) {
+            *reinterpret_cast<volatile int *>(&ctl.term) = i;
+            __threadfence_block();
+          }
+          mbar_arrive_warp(&ctl.afull[st]);
+        }
+        break;
+      }
+      unsigned char *arow = sA + st * 16384;
+      const bool wdone = __all_sync(0xffffffffu, ps.P <= GAGS_T_STOP);
+      if (wdone) {
+        if (lane == 0) atomicAdd(&ctl.skip[st], 1);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = z;
+      } else {
+        float4 av[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          av[c] = *reinterpret_cast<const float4 *>(arow + sw128(rowoff + c * 16));
+        int lastk = -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 h, l;
+          tc3_chain8(av[2 * c], av[2 * c + 1], c * 8, ps, lastk, h, l);
+          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = h;
+          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + (c + 4) * 16)) = l;
+        }
+        if (lastk >= 0) ps.last = ctl.lidx[st][pw][lastk];
+      }
+      if (warp == 0) TC_STAMP(0, i, 2);
+      fence_async_smem();
+      mbar_arrive_warp(&ctl.full[st]);
+      if (cache) mbar_arrive_warp(&ctl.afull[st]);
+      if (warp == 0) TC_STAMP(0, i, 3);
+      if (!counted && __all_sync(0xffffffffu, ps.P <= GAGS_T_STOP)) {
+        counted = true;
+        if (lane == 0) {
+          *reinterpret_cast<volatile int *>(&ctl.wdone[pw]) = 1;
+          atomicMax(&ctl.skip_from, i + 1);
+          __threadfence_block();
+          atomicAdd(&ctl.done_warps, 1);
+        }
+      }
+    }
+    ctl.Tfin[tid] = ps.T;
+    if (inside && ch0 == 0) {
+      const size_t pix = (size_t)pyi * W + pxi;
+      alphas[pix] = 1.f - ps.T;
+      last_ids[pix] = ps.last;
+    }
+    if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
+  } else if (V3 && warp < 8) {
+    // ======================= v3 front warps: scanner + alpha evaluation ============================
+    // lane = Gaussian of the batch: the record stays in registers and the warp evaluates the 32
+    // alphas of ITS 8x4 pixel block (front warp w <-> chain warp w), all independent
+    const int p = tid - 128;
+    const int fw = warp - 4;
+    TcScanner sc;
+    sc.init(geom, ids, s, e, (float)x0 + 0.5f, (float)y0 + 0.5f, rg0, rg1, rgid, ctl.wcnt, p);
+    if (sc.scan < e) sc.issue();
+    const float pxc = (float)(x0 + ((fw & 1) << 3)) + 0.5f;
+    const float pyc = (float)(y0 + ((fw >> 1) << 2)) + 0.5f;
+    for (int i = 0;; ++i) {
+      const int st = i & 1;
+      if (warp == 4) TC_STAMP(3, i + 1, 0);
+      const int dw = *reinterpret_cast<volatile int *>(&ctl.done_warps);
+      const bool stop_all = named_bar_or(1, 128, dw == 4);
+      while (!stop_all && sc.queued() < KB && sc.more()) {
+        if (!sc.pending) sc.issue();
+        sc.finish();
+      }
+      if (warp == 4) TC_STAMP(3, i + 1, 1);
+      const int nb = stop_all ? 0 : min(KB, sc.queued());
+      if (!sc.pending && nb > 0 && (sc.queued() - nb) < KB && sc.scan < e) sc.issue();
+      // stage reuse: the MMA of batch i-2 has read A / B / gid, and (training) its tile has left A
+      if (i >= 2) {
+        mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+        if (cache) mbar_wait_bounded(&ctl.sdone[st], ((i >> 1) - 1) & 1);
+      }
+      // this lane's Gaussian of the batch, straight from the survivor ring
+      TcFrontRec fr;
+      fr.mx = fr.my = fr.A = fr.B = fr.C = fr.op = 0.f;
+      int gid = -1, lidx = 0;
+      if (lane < nb) {
+        const int slot = (sc.qhead + lane) & (RING - 1);
+        const float4 g0 = rg0[slot], g1 = rg1[slot];
+        const TcRec r = tc_make_rec(g0, g1);
+        fr.mx = r.q0.x; fr.my = r.q0.y; fr.A = r.q0.z; fr.B = r.q0.w; fr.C = r.q1.x; fr.op = r.q1.y;
+        lidx = __float_as_int(g1.z);
+        gid = rgid[slot];
+      }
+      // chain warp w only synchronises with front warp w: each front warp leaves its own copy of
+      // what its partner reads (nb and the list indices are uniform over the front group)
+      ctl.lidx[st][fw][lane] = lidx;
+      if (lane == 0) ctl.nbw[st][fw] = nb;
+      if (fw == 0) {
+        if (lane == 0) ctl.gcount[st] = nb;
+        ctl.gid[st][lane] = gid;
+        if (cache && nb > 0) wmeta[(size_t)(hbase + i) * KB + lane] = gid;
+      }
+      mbar_arrive_warp(&ctl.list[st]);
+      if (warp == 4) TC_STAMP(3, i + 1, 2);
+      if (nb > 0 && *reinterpret_cast<volatile int *>(&ctl.wdone[fw]) == 0)
+        tc3_front_alphas(fr, pxc, pyc, sA + st * 16384 + fw * 4096, lane);
+      mbar_arrive_warp(&ctl.alpha[st][fw]);
+      if (nb == 0) break;
+      sc.qhead += nb;
+    }
+  } else if (warp < 4) {
     // ======================= pixel warps: one thread per pixel =====================================
     const int pw = warp;
     const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
@@ -490,7 +629,10 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   if (warp == 12) tmem_dealloc<L::TCOLS>(tb);
 }
 
-template <int NATOM>
+// 2 = one thread per pixel evaluates alpha and the chain (round-1 kernel); 3 = front / chain split.
+int g_fwd_variant = 3;
+
+template <int NATOM, bool V3>
 int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
               int H, const int *offsets, const int *ids, float *render, float *alphas,
               int *last_ids, unsigned char *wcache, int *wmeta, int *wlist, int *wcount,
@@ -498,20 +640,24 @@ int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, c
   using L = TcLayout<NATOM>;
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(blend_fwd_tc<NATOM>,
+  {   // per-device attribute: set on every launch (a process may drive several GPUs)
+    cudaError_t e = cudaFuncSetAttribute(blend_fwd_tc<NATOM, V3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
-  blend_fwd_tc<NATOM><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
+  blend_fwd_tc<NATOM, V3><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
       reinterpret_cast<const float4 *>(geom), colors, D, ch0, nch, bg, W, H, tw, offsets, ids,
       render, alphas, last_ids, wcache, wmeta, wlist, wcount);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
+
+extern "C" int gags_set_fwd_variant(int32_t v) {
+  if (v != 2 && v != 3) return GAGS_EINVAL;
+  g_fwd_variant = v;
+  return 0;
+}
 
 // Tensor-core wide forward: 32 < D, D % 16 == 0.  Channels are processed 256 per launch.  When
 // `wcache` is non-NULL the first launch also saves every batch's weight tile (+ Gaussian ids) for
@@ -528,11 +674,20 @@ int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const f
     int rc;
 #define GAGS_TC_ARGS geom, colors, D, ch0, nch, background, width, height, offsets, flatten_ids, \
                      render, alphas, last_ids, wc, wmeta, wlist, wcount, st
-    switch (natom) {
-      case 1: rc = launch_tc<1>(GAGS_TC_ARGS); break;
-      case 2: rc = launch_tc<2>(GAGS_TC_ARGS); break;
-      case 3: rc = launch_tc<3>(GAGS_TC_ARGS); break;
-      default: rc = launch_tc<4>(GAGS_TC_ARGS); break;
+    if (g_fwd_variant == 2) {
+      switch (natom) {
+        case 1: rc = launch_tc<1, false>(GAGS_TC_ARGS); break;
+        case 2: rc = launch_tc<2, false>(GAGS_TC_ARGS); break;
+        case 3: rc = launch_tc<3, false>(GAGS_TC_ARGS); break;
+        default: rc = launch_tc<4, false>(GAGS_TC_ARGS); break;
+      }
+    } else {
+      switch (natom) {
+        case 1: rc = launch_tc<1, true>(GAGS_TC_ARGS); break;
+        case 2: rc = launch_tc<2, true>(GAGS_TC_ARGS); break;
+        case 3: rc = launch_tc<3, true>(GAGS_TC_ARGS); break;
+        default: rc = launch_tc<4, true>(GAGS_TC_ARGS); break;
+      }
     }
 #undef GAGS_TC_ARGS
     if (rc != 0) return rc;

@@ -165,6 +165,82 @@ __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
   split_pack2(w[6], w[7], hi.w, lo.w);
 }
 
+// ---- v3 split of the weight evaluation -----------------------------------------------------------
+// The per-pixel work above has two very different halves: the alpha evaluation (independent across
+// Gaussians and pixels, ~60 % of the instructions, needs the Gaussian record) and the transmittance
+// chain (sequential in the Gaussian index, needs nothing but the alphas).  The v3 forward runs them
+// in two warp groups, one batch apart:
+//   front warps (lane = GAUSSIAN of the batch, record in registers, no shared-memory reads): the 32
+//       alphas of the warp's 8x4 pixel block, written as fp32 into the pixel rows of the A stage;
+//   chain warps (lane = PIXEL): read their own 128-B row (32 alphas), run the chain and overwrite
+//       the row in place with the [hi(32) | lo(32)] bf16 weights the MMA reads.
+// Same operations in the same order as tc_weights8, so the two variants are bit-identical.
+//
+// alpha_k of pixel row r lives at logical byte 4k of the row; rows are stored with the A tile's
+// SWIZZLE_128B pattern (16-B chunk index XOR row % 8) so that both the lane-per-Gaussian stores and
+// the lane-per-pixel 16-B loads are bank-conflict free.
+struct TcFrontRec {
+  float mx, my, A, B, C, op;
+};
+// `rowbase` = shared address of pixel row 0 of this warp's block (rows are 128 B, block = 32 rows:
+// row y*8 + x <-> pixel (x, y) of the 8x4 block); (pxc, pyc) = centre of the block's first pixel.
+__device__ __forceinline__ void tc3_front_alphas(const TcFrontRec &g, float pxc, float pyc,
+                                                 unsigned char *rowbase, int lane) {
+  float dx[8], m[8];
+  uint32_t off[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    dx[x] = g.mx - (pxc + (float)x);
+    m[x] = g.A * dx[x];
+    off[x] = (uint32_t)x * 128u + ((uint32_t)((lane >> 2) ^ x) << 4) + ((uint32_t)(lane & 3) << 2);
+  }
+#pragma unroll
+  for (int y = 0; y < 4; ++y) {
+    const float dy = g.my - (pyc + (float)y);
+    const float u = (g.C * dy) * dy;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const float t = fmaf(g.B, dy, m[x]);
+      const float q = fmaf(t, dx[x], u);
+      const float al = fminf(GAGS_ALPHA_MAX, g.op * tc_ex2(q));
+      const float a = (q <= 0.f && al >= GAGS_ALPHA_MIN) ? al : 0.f;
+      *reinterpret_cast<float *>(rowbase + y * 1024 + off[x]) = a;
+    }
+  }
+}
+
+struct TcChain {
+  float P, T;
+  int last;
+};
+// 8 consecutive alphas of the batch (positions k0 .. k0+7) at one pixel -> bf16 hi / lo chunks;
+// `lastk` receives the in-batch position of the last contributor (unchanged when there is none).
+__device__ __forceinline__ void tc3_chain8(const float4 &a0, const float4 &a1, int k0, TcChain &st,
+                                           int &lastk, uint4 &hi, uint4 &lo) {
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float P[9];
+  P[0] = st.P;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) P[k + 1] = fmaf(-a[k], P[k], P[k]);
+  float w[8];
+  float T = st.T;
+  int lk = lastk;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool alive = P[k + 1] > GAGS_T_STOP;
+    w[k] = alive ? a[k] * P[k] : 0.f;
+    T = alive ? P[k + 1] : T;
+    lk = (w[k] > 0.f) ? (k0 + k) : lk;
+  }
+  st.P = P[8];
+  st.T = T;
+  lastk = lk;
+  split_pack2(w[0], w[1], hi.x, lo.x);
+  split_pack2(w[2], w[3], hi.y, lo.y);
+  split_pack2(w[4], w[5], hi.z, lo.z);
+  split_pack2(w[6], w[7], hi.w, lo.w);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Scanner: per-thread state of the NT-thread warp group that walks a tile's depth-sorted list NT
 // entries at a time, culls every Gaussian whose alpha >= 1/255 bounding box misses the half tile

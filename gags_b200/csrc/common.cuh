@@ -26,6 +26,19 @@
 
 static inline bool gags_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
+// SM count of the current device (148 on B200), cached per device: grids are sized in multiples of it.
+static inline long long gags_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // Device-side copy of gags_camera_t plus the tile grid (passed by value as a kernel parameter).
 struct CamDev {
   float R[9];

@@ -272,7 +272,7 @@ extern "C" int gags_scale_inplace(float *v, const float *scale_dev, int64_t nume
   if (numel == 0) return 0;
   const long long n4 = numel / 4;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 4) blocks = 148LL * 4;
+  if (blocks > gags_sm_count() * 4) blocks = gags_sm_count() * 4;
   scale_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float4 *>(v), scale_dev, n4);
   GAGS_CHECK_LAUNCH();
@@ -288,7 +288,7 @@ extern "C" int gags_l1_loss_fused(const float *render, const float *target, cons
   if (HW == 0) return 0;
   const long long n4 = (long long)HW * (D / 4);
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 8) blocks = 148LL * 8;     // 8 resident 256-thread CTAs per SM, grid-stride
+  if (blocks > gags_sm_count() * 8) blocks = gags_sm_count() * 8;     // 8 resident 256-thread CTAs per SM, grid-stride
   l1_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(render), reinterpret_cast<const float4 *>(target), mask, n4,
       D / 4, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
@@ -307,7 +307,7 @@ extern "C" int gags_l1_loss_segmap(const float *render, const int32_t *seg, cons
   if (HW == 0) return 0;
   const long long n4 = (long long)HW * (D / 4);
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  if (blocks > gags_sm_count() * 8) blocks = gags_sm_count() * 8;
   l1_loss_segmap_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(render), seg, reinterpret_cast<const float4 *>(emb), mask, n4,
       D / 4, n_seg, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
@@ -334,7 +334,7 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   if (n4 > 0) {
     long long blocks = (n4 + 255) / 256;
     // half of each SM's thread slots stay free next to this pure HBM stream
-    if (blocks > 148LL * 4) blocks = 148LL * 4;
+    if (blocks > gags_sm_count() * 4) blocks = gags_sm_count() * 4;
     adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),
         reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), n4, step_size,
@@ -389,7 +389,7 @@ extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  const long long cap_u = 148LL * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 4);
+  const long long cap_u = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 4);
   if (blocks > cap_u) blocks = cap_u;                          // default: half the thread slots free
 #define GAGS_PEER_LAUNCH(MAXW)                                                                   \
   adam_peer_kernel<MAXW><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                      \
@@ -424,7 +424,7 @@ extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  const long long cap_m = 148LL * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
+  const long long cap_m = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
   if (blocks > cap_m) blocks = cap_m;                          // small grid, 4 reductions per thread
   adam_multicast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),
@@ -460,7 +460,7 @@ extern "C" int gags_zero_fill(void *ptr, int64_t bytes, void *stream) {
   if (!gags_aligned16(ptr) || (bytes & 15)) return GAGS_EALIGN;
   const long long n4 = bytes / 16;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148LL * 2) blocks = 148LL * 2;
+  if (blocks > gags_sm_count() * 2) blocks = gags_sm_count() * 2;
   zero_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float4 *>(ptr), n4);
   GAGS_CHECK_LAUNCH();

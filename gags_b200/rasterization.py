@@ -472,8 +472,10 @@ def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
     """The [N, D] buffer the feature backward accumulates into, and the leaf it belongs to when the
     reduction goes straight into `.grad` (direct_grad_accumulation)."""
     sink = ctx.sink if (need_col and not need_geo) else None
-    if sink is not None and sink.grad is not None and sink.grad.is_contiguous() \
-            and sink.grad.dtype == torch.float32:
+    if sink is not None and sink.grad is not None and not (
+            sink.grad.is_contiguous() and sink.grad.dtype == torch.float32):
+        sink = None                              # cannot reduce in place: autograd adds the result
+    if sink is not None and sink.grad is not None:
         v_colors = sink.grad                     # accumulate in place: nothing to zero or add
         ctx.prezero = None
         ev = sink_ready_events.pop(v_colors.data_ptr(), None)
@@ -526,7 +528,9 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
     _C.require_cuda(seg_hw, emb)
     dev = r.device
     sg, em = seg_hw.contiguous(), emb.contiguous()
-    m = mask_hw.to(torch.float32).contiguous().reshape(-1) if mask_hw is not None else None
+    from .utils.loss_utils import _mask_f32
+    _C.require_cuda(mask_hw)
+    m = _mask_f32(mask_hw, height, width)
     need_col = h.cols.requires_grad
     _mark("bwd_start")
     v_colors, sink = _take_grad_buffer(ctx, True, False, N, D, dev)

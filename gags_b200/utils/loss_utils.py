@@ -24,17 +24,28 @@ def cos_loss(network_output, gt):
     return 1 - F.cosine_similarity(network_output, gt, dim=0).mean()
 
 
+def _mask_f32(mask_hw, H: int, W: int):
+    """[H,W] / [1,H,W] mask of any dtype (bool included) -> contiguous float32 [H*W], or None."""
+    if mask_hw is None:
+        return None
+    if mask_hw.numel() != H * W:
+        raise ValueError(f"mask must have H*W = {H * W} elements, got shape {tuple(mask_hw.shape)}")
+    return mask_hw.to(torch.float32).contiguous().reshape(-1)
+
+
 class _L1Fused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, render_hwd, target_hwd, mask_hw, seg_hw=None, emb=None):
         """Dense target `target_hwd` [H,W,D], or (target_hwd=None) the compact pair seg_hw [H,W]
         int32 + emb [n_seg, D]."""
-        _C.require_cuda(render_hwd, target_hwd, emb)
+        _C.require_cuda(render_hwd, target_hwd, emb, mask_hw, seg_hw)
         if render_hwd.dim() != 3:
             raise ValueError("render must be [H,W,D]")
         r = render_hwd.contiguous()
         H, W, D = r.shape
-        m = mask_hw.contiguous().reshape(-1) if mask_hw is not None else None
+        # the kernel reads the mask as float32 [H*W]; the reference's seg_mask is a bool [1,H,W]
+        # tensor (scene/dataset_readers.py:118-121), so convert and check the size here
+        m = _mask_f32(mask_hw, H, W)
         loss = torch.zeros(1, dtype=torch.float32, device=r.device)
         v = torch.empty_like(r)
         numel = float(H * W * D)

@@ -276,6 +276,11 @@ int gags_adam_step_multicast(const float *mc_grad, float *mc_param, const float 
  * multicast).  Process-wide; used by tools/peer_rate.py.                                         */
 int gags_set_peer_grid(int32_t ctas_per_sm);
 
+/* Tuning hook: wide forward blend variant.  3 (default) = alpha evaluation (lane = Gaussian) and
+ * transmittance chain (lane = pixel) in two warp groups; 2 = one thread per pixel does both (the
+ * round-1 kernel).  Bit-identical outputs; process-wide; used by the parity tests and bench.      */
+int gags_set_fwd_variant(int32_t variant);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);
