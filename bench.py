@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — views/sec of the GAGS distillation step on synthetic Gaussians (BASELINE.json metric).
+"""bench.py — views/sec of the GAGS feature-rasterisation hot path on synthetic Gaussians
+(BASELINE.json metric and configs).
 
-  python bench.py --gpus N --steps K --warmup W            # product arm (sm_100a kernels)
-  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU oracle port
-  torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU, view-parallel
+  python bench.py --gpus N --steps K --warmup W              # product arm (sm_100a kernels), config 3
+  python bench.py --config {1,2,5} ...                       # the other BASELINE.json configs
+  python bench.py --impl reference   ...                     # reference arm: the CPU oracle port
+  python bench.py --impl restatement ...                     # gsplat-algorithm restatement (CUDA, ours)
+  torchrun ... bench.py --gpus N ...                         # N > 1: one rank per GPU, view-parallel
 
-One step = one optimiser step of the train.py loop (/root/reference/train.py:109-228) with frozen
-geometry on the config-3 shape (N=2M Gaussians, 1080x1920, D=256): for each of `views_per_step`
-views per rank (default 1 at every N)  render() -> L1 against the view's emb[seg] target fused with
-the backward to the per-Gaussian features (l1_backward_fused);  then Adam on the feature table —
-at N>1 fused with the gradient all-reduce and the parameter all-gather into one NVLink peer-memory
-kernel (parallel.PeerAdam; --nccl-allreduce = NCCL all-reduce + local Adam, also the fallback).
+Configs 3/4/5 (training): one step = one optimiser step of the train.py loop
+(/root/reference/train.py:109-228) with frozen geometry: for each of `views_per_step` views per rank
+(default 1 at every N)  render() -> L1 against the view's emb[seg] target fused with the backward to
+the per-Gaussian features (l1_backward_fused);  then Adam on the feature table — at N > 1 fused with
+the gradient all-reduce and the parameter all-gather into one NVLink peer-memory kernel
+(parallel.PeerAdam; --nccl-allreduce = NCCL all-reduce + local Adam, also the fallback).
+Configs 1/2 (forward only): one step = one render() under no_grad.
+
 value = views/sec over the whole job (all ranks), inputs resident in HBM.
-e2e   = the same loop with the per-view training target (segment map + embedding table, the
-        inputs of the reference's read_sam_clip_feature) copied from pinned host memory each view
-        and the loss read back to the host each step.
+e2e   = the same loop through the public API with HOST inputs: training — the per-view target
+        (segment map + embedding table, the inputs of read_sam_clip_feature) copied from pinned host
+        memory every view and the loss read back every step; forward-only — the camera pose copied
+        in and the rendered map copied out to pinned host memory every view (render.py:118-122).
+Extra keys of the config-3 line at N = 1: value_fwd_bwd (no optimiser pass), dense_target (the
+Appendix-B dense random [H,W,D] target instead of the compact one), cuda_baseline (the labelled
+gsplat-algorithm restatement timed in the same run).  At N > 1: exchange_check.
 """
 from __future__ import annotations
 
@@ -28,7 +37,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "views/sec fwd+bwd (N=2M Gaussians, 1080p, D=256)"      # config 3, the headline
+METRICS = {
+    1: "views/sec fwd (N=10k Gaussians, 256x256, D=3 RGB)",
+    2: "views/sec fwd-only (N=500k Gaussians, 720p, D=32)",
+    3: "views/sec fwd+bwd (N=2M Gaussians, 1080p, D=256)",      # the headline (BASELINE.json)
+    4: "views/sec fwd+bwd (N=2M Gaussians, 1080p, D=256)",
+    5: "views/sec fwd+bwd (N=5M Gaussians, 1440p, D=512)",
+}
+FWD_ONLY = {1: True, 2: True, 3: False, 4: False, 5: False}
 
 
 def parse():
@@ -36,18 +52,39 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="gags_b200", choices=["gags_b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = headline)")
+    ap.add_argument("--impl", default="gags_b200", choices=["gags_b200", "reference", "restatement"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(METRICS),
+                    help="BASELINE.json config id (3 = headline)")
+    ap.add_argument("--fwd-only", action="store_true", help="render() only (default for configs 1, 2)")
     ap.add_argument("--views-per-step", type=int, default=None,
-                    help="views rendered per rank between optimiser steps (default 1; 4 when N>1)")
+                    help="views rendered per rank between optimiser steps (default 1 at every N)")
     ap.add_argument("--n", type=int, default=None, help="override N (debug only; invalidates value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip value_fwd_bwd / dense_target / cuda_baseline / exchange_check")
+    ap.add_argument("--lean", action="store_true", help="= --no-e2e --no-cpu-baseline --no-extras")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="N>1: NCCL all-reduce + local Adam instead of the fused peer-memory step")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="separate L1 kernel + autograd backward instead of l1_backward_fused")
-    return ap.parse_args()
+    ap.add_argument("--cpu-tiles", type=int, default=256, help="tiles sampled by the CPU baseline")
+    a = ap.parse_args()
+    if a.lean:
+        a.no_e2e = a.no_cpu_baseline = a.no_extras = True
+    if FWD_ONLY[a.config]:
+        a.fwd_only = True
+    return a
+
+
+def workload_string(cfg: int, n: int, H: int, W: int, D: int, fwd_only: bool) -> str:
+    if fwd_only:
+        what = "render() forward only (no_grad)" + (", RGB through SH degree 3" if D == 3 else
+                                                    ", feature mode")
+    else:
+        what = ("render + fused L1 vs emb[seg] target + feature backward + fused Adam "
+                "(frozen geometry)")
+    return f"config{cfg}: N={n}, {H}x{W}, D={D}, {what}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -96,31 +133,36 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 def reference_arm(args):
     """The reference's implementation of this path (gsplat) is CUDA-only and absent; its CPU
-    stand-in is the oracle port, timed on all host cores on a bounded sample of the workload."""
+    stand-in is the oracle port, timed on all host cores on a bounded sample of the workload:
+    projection + keys + sort + offsets on ALL N Gaussians, blend forward (+ feature backward for the
+    training configs) on `--cpu-tiles` sampled tiles, extrapolated to the tile grid."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     from gags_b200.synthetic import CONFIGS, config_scene
     from oracle.cpu_baseline import time_view
     n, h, w, d = CONFIGS[args.config]
-    scene = config_scene(args.config)
+    scene = config_scene(args.config, with_sh=(d == 3))
     times, info = [], None
+    t_all = time.time()
     for i in range(args.warmup + args.steps):
-        info = time_view(scene, scene.cameras[i % len(scene.cameras)], d, n_tiles=24, seed=i)
+        info = time_view(scene, scene.cameras[i % len(scene.cameras)], d, n_tiles=args.cpu_tiles,
+                         seed=i, backward=not args.fwd_only)
         if i >= args.warmup:
             times.append(info["seconds_per_view"])
-        if sum(times) > 150:
+        if time.time() - t_all > 150 and times:
             break
     sec = sum(times) / len(times)
-    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": "views/s",
-            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+    line = {"impl": "reference", "metric": METRICS[args.config], "value": 1.0 / sec,
+            "unit": "views/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config{args.config}: N={n}, {h}x{w}, D={d}, fwd+bwd_feat, "
-                                   "CPU oracle port (gsplat itself is CUDA-only and not installed)"},
+            "config": {"workload": workload_string(args.config, n, h, w, d, args.fwd_only)
+                       + " — CPU oracle port (gsplat itself is CUDA-only and not installed)"},
             "cpu_baseline": {"value": 1.0 / sec, "unit": "views/s", "cores": info["cores"],
-                             "kind": "port", "sample": info["sample"]},
+                             "kind": "port", "sample": info["sample"], "geom_s": info["geom_s"],
+                             "blend_s_extrapolated": info["blend_s_extrapolated"],
+                             "tile_ms_p10_p50_p90": info["tile_ms_p10_p50_p90"]},
             "e2e": {"value": 1.0 / sec, "unit": "views/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -135,14 +177,14 @@ def main():
 
     import torch
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=gags_b200) needs a CUDA device: there is no CPU fallback")
+        raise SystemExit(f"bench.py (impl={args.impl}) needs a CUDA device: there is no CPU fallback")
     import torch.distributed as dist
     from gags_b200 import _C, parallel, rasterization as R
     from gags_b200.arguments import OptimizationParams
     from gags_b200.gaussian_renderer import render
     from gags_b200.scene import GaussianModel
-    from gags_b200.synthetic import CONFIGS, config_scene
-    from gags_b200.utils.loss_utils import l1_backward_fused, l1_loss_segmap_fused
+    from gags_b200.synthetic import CONFIGS, config_scene, make_target
+    from gags_b200.utils.loss_utils import l1_backward_fused, l1_loss_fused, l1_loss_segmap_fused
 
     rank, world, local = parallel.init_from_env("nccl")
     if world != args.gpus and world > 1:
@@ -152,9 +194,13 @@ def main():
     # one view per rank per optimiser step at every N (the train.py loop on each rank): per-GPU work
     # is the same at 1, 2, 4 and 8 GPUs; --views-per-step k accumulates k views before the exchange
     kviews = args.views_per_step or 1
+    cfg = args.config
+    fwd_only = args.fwd_only
+    restate = args.impl == "restatement"
 
-    n, H, W, D = CONFIGS[args.config]
-    scene = config_scene(args.config)
+    n, H, W, D = CONFIGS[cfg]
+    rgb = D == 3
+    scene = config_scene(cfg, with_sh=rgb)
     if args.n:
         n = args.n
         for f in ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest",
@@ -163,7 +209,8 @@ def main():
     pc = GaussianModel(3, device=dev)
     pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
                            scene.features_dc, scene.features_rest, scene.semantic_feature)
-    pc.training_setup(OptimizationParams(), fused_optimizer=True)
+    pc.active_sh_degree = 3
+    pc.training_setup(OptimizationParams(), fused_optimizer=not restate)
     cams = [c.to(dev) for c in scene.cameras]
     n_views = len(cams)
     # the cameras are loaded once and never written again (scene/cameras.py:58): tell the renderer,
@@ -175,14 +222,15 @@ def main():
     # (seg_map, img_embed) inputs to read_sam_clip_feature (scene/dataset_readers.py:54-121).
     n_targets, n_seg = 2, 256
     g = torch.Generator().manual_seed(4321)
-    seg_host = [torch.randint(0, n_seg, (H // 8 + 1, W // 8 + 1), generator=g, dtype=torch.int32)
-                .repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].contiguous().pin_memory()
-                for _ in range(n_targets)]
-    emb_host = [(0.1 * torch.randn(n_seg, D, generator=g)).pin_memory() for _ in range(n_targets)]
-
-    # the targets stay in that compact form on the device as well: the fused loss gathers
-    # emb[seg] on the fly (the reference materialises the dense map every iteration, train.py:162)
-    targets_dev = [(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
+    seg_host, emb_host, targets_dev = [], [], []
+    if not fwd_only:
+        seg_host = [torch.randint(0, n_seg, (H // 8 + 1, W // 8 + 1), generator=g, dtype=torch.int32)
+                    .repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].contiguous().pin_memory()
+                    for _ in range(n_targets)]
+        emb_host = [(0.1 * torch.randn(n_seg, D, generator=g)).pin_memory() for _ in range(n_targets)]
+        # the targets stay in that compact form on the device as well: the fused loss gathers
+        # emb[seg] on the fly (the reference materialises the dense map every iteration, train.py:162)
+        targets_dev = [(s.to(dev), e.to(dev)) for s, e in zip(seg_host, emb_host)]
 
     # k views per optimiser step: let the backward reduce straight into .grad (see rasterization.py)
     R.direct_grad_accumulation = kviews > 1
@@ -192,12 +240,12 @@ def main():
     # all-reduce pipelined with the full local Adam pass), which is also the fallback when
     # symmetric memory cannot be set up on this box.
     peer, exchange = None, "none"
-    if world > 1:
+    if world > 1 and not fwd_only:
         exchange = "nccl-allreduce + local Adam"
         if not args.nccl_allreduce:
             try:
-                grp = next(g for g in pc.optimizer.param_groups
-                           if any(q is pc._semantic_feature for q in g["params"]))
+                grp = next(g_ for g_ in pc.optimizer.param_groups
+                           if any(q is pc._semantic_feature for q in g_["params"]))
                 peer = parallel.PeerAdam(pc._semantic_feature, lr=grp["lr"], betas=grp["betas"],
                                          eps=grp["eps"])
                 exchange = ("peer-memory fused all-reduce + sharded Adam + all-gather (one kernel, "
@@ -209,8 +257,14 @@ def main():
     if peer is not None:
         R.direct_grad_accumulation = True
 
+    # ---- the steps ------------------------------------------------------------------------------
+    def render_view(cam):
+        if rgb:
+            return render(cam, pc, None, bg, False)          # SH colours (config 1)
+        return render(cam, pc, None, bg)                     # feature_mode=True (default)
+
     def one_view(cam, target, target_ready=None):
-        pkg = render(cam, pc, None, bg)                      # feature_mode=True (default)
+        pkg = render_view(cam)
         if target_ready is not None:                         # the target's H2D copy (copy stream)
             torch.cuda.current_stream(dev).wait_event(target_ready)
         if args.unfused_loss:
@@ -232,16 +286,46 @@ def main():
 
     def step_resident(step):
         loss = None
+        if fwd_only:
+            with torch.no_grad():
+                for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+                    loss = render_view(cams[v])["render"]
+            return loss
         for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
             loss = one_view(cams[v], targets_dev[v % n_targets])
         opt_step()
         return loss
 
+    def step_no_adam(step):
+        """fwd + loss + bwd only (§8d: 'Adam step reported separately')."""
+        loss = None
+        for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+            loss = one_view(cams[v], targets_dev[v % n_targets])
+        pc._semantic_feature.grad = None
+        return loss
+
     copy_stream = torch.cuda.Stream(device=dev)
+    out_host = None
+    cam_host = [c.world_view_transform.cpu().pin_memory() for c in cams] if fwd_only else None
 
     def step_e2e(step):
+        nonlocal out_host
         loss = None
-        h2d = 0
+        h2d = d2h = 0
+        if fwd_only:
+            import copy
+            with torch.no_grad():
+                for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+                    cam = copy.copy(cams[v])
+                    cam.world_view_transform = cam_host[v].to(dev, non_blocking=True)   # pose in
+                    h2d += 64
+                    img = render_view(cam)["render"]
+                    if out_host is None:
+                        out_host = torch.empty(img.shape, dtype=img.dtype).pin_memory()
+                    out_host.copy_(img, non_blocking=True)                              # map out
+                    d2h += img.numel() * 4
+            torch.cuda.current_stream(dev).synchronize()
+            return float(out_host.view(-1)[0]), h2d, d2h
         for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
             cam = cams[v]                 # cameras live on the device (scene/cameras.py:58)
             # this view's target travels on a copy stream while the view renders; the loss waits
@@ -256,7 +340,7 @@ def main():
             h2d += seg.numel() * 4 + emb.numel() * 4
             loss = one_view(cam, (seg, emb), ready)
         opt_step()
-        return float(loss.item()), h2d                       # D2H read of the step's loss
+        return float(loss.item()), h2d, 4                    # D2H read of the step's loss
 
     def barrier():
         if world > 1:
@@ -292,6 +376,10 @@ def main():
                       "device_allocs": torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - a0}
         return ms, last, sampler.summary(), _C.launches() - l0
 
+    # =============================================================================================
+    if restate:
+        return restatement_arm(args, locals())
+
     # Untimed priming (like the reference's scene loading): the grow-only workspaces (intersection
     # buffers, weight-tile cache) reach their steady size, so that no cudaMalloc — a device-wide
     # sync — lands in the timed region.  The W warm-up and K timed steps follow as the contract says.
@@ -306,14 +394,28 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        ms_e, last, _, _ = timed(step_e2e, max(3, args.steps // 2), 2)
         steps_e = max(3, args.steps // 2)
+        ms_e, last, _, _ = timed(step_e2e, steps_e, 2)
         e2e = {"value": steps_e * kviews * world / (ms_e * 1e-3), "unit": "views/s",
-               "h2d_bytes_per_step": int(last[1]), "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": int(last[1]), "d2h_bytes_per_step": int(last[2])}
 
     if peer is not None:
         peer.synchronize()
         torch.cuda.synchronize(dev)
+
+    extras = {}
+    # ---- fwd + loss + bwd only, and the Appendix-B dense-target variant (N = 1, training) ---------
+    if not args.no_extras and not fwd_only and world == 1:
+        for i in range(3):
+            step_no_adam(20_000 + i)
+        ms_fb, _, _, _ = timed(step_no_adam, max(5, args.steps // 2), 2)
+        extras["value_fwd_bwd"] = {"value": max(5, args.steps // 2) * kviews / (ms_fb * 1e-3),
+                                   "unit": "views/s",
+                                   "note": "render + fused L1 + feature backward, no optimiser pass"}
+        if cfg in (3, 4):
+            extras["dense_target"] = dense_target_leg(locals())
+            torch.cuda.empty_cache()
+
     # ---- per-stage device times for the roofline (rank 0, single views, CUDA events) -------------
     stage_ms, stats, roofline = {}, {}, None
     if rank == 0:
@@ -326,21 +428,32 @@ def main():
         peak_kind = "measured" if peaks else "fallback"
         acc = {}
         reps = 5
-        for i in range(-2, reps):                 # two unrecorded passes: this single-stream,
+        saved_direct = R.direct_grad_accumulation
+        if peer is not None:
+            R.direct_grad_accumulation = False     # the instrumented single-GPU pass uses its own buffer
+            pc._semantic_feature.grad = None
+        for i in range(-3, reps):                 # three unrecorded passes: this single-stream,
             R.stage_events = []                   # instrumented path has its own allocation pattern
             cam = cams[(7 * i) % n_views]
-            pkg = render(cam, pc, None, bg)
-            R._mark("loss_start")
-            if args.unfused_loss:
-                loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
-                R._mark("loss")
-                loss.backward()
+            if fwd_only:
+                with torch.no_grad():
+                    pkg = render_view(cam)
             else:
-                loss = l1_backward_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
-            R._mark("backward_end")
-            pc.optimizer.step()
-            R._mark("adam")
-            pc.optimizer.zero_grad(set_to_none=True)
+                pkg = render_view(cam)
+                R._mark("loss_start")
+                if args.unfused_loss:
+                    loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
+                    R._mark("loss")
+                    loss.backward()
+                else:
+                    loss = l1_backward_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
+                R._mark("backward_end")
+                if peer is None:
+                    pc.optimizer.step()
+                    R._mark("adam")
+                    pc.optimizer.zero_grad(set_to_none=True)
+                else:
+                    pc._semantic_feature.grad = None
             torch.cuda.synchronize()
             ev = R.stage_events
             R.stage_events = None
@@ -351,7 +464,12 @@ def main():
             if i == 0:
                 radii = pkg["radii"]
                 stats["n_visible"] = int((radii > 0).sum())
-        stage_ms = {k: sum(v) / len(v) for k, v in acc.items()}
+        if peer is not None:
+            R.direct_grad_accumulation = saved_direct
+            pc._semantic_feature.grad = peer.grad
+        # min over the repetitions: a cudaMalloc that lands inside one instrumented pass (this path
+        # allocates differently from the timed loop) must not be booked as kernel time
+        stage_ms = {k: min(v) for k, v in acc.items()}
         nv = stats.get("n_visible", n)
         fwd_bytes = nv * 4 * D + H * W * (4 * D + 8)
         bwd_bytes = H * W * (4 * D + 8) + nv * 4 * D
@@ -359,52 +477,314 @@ def main():
             else "blend_bwd"
         kbytes = fwd_bytes if kname == "blend_fwd" else bwd_bytes
         ach = kbytes / (stage_ms[kname] * 1e-3) / 1e9
-        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-        # (profiles/traffic.json, written by tools/ncu_summary.py); config 3 only
-        traffic = None
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
+        # round (profiles/traffic.json, written by tools/ncu_summary.py); config 3 only.  The
+        # forward's weight-tile cache writes are an intermediate, reported separately.
+        traffic = non_alg = None
         try:
-            if args.config in (3, 4):
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kname]
+            if cfg in (3, 4):
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tj[kname]
+                non_alg = tj.get(kname + "_non_algorithmic")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "peak_kind": peak_kind,
-                    "traffic": traffic, "algorithmic_bytes": kbytes,
-                    "avg_launch_ms": stage_ms[kname]}
-        step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4) + H * W * (4 * D + 8) + n * (4 * D + 24)
+                    "traffic": traffic, "non_algorithmic_bytes": non_alg,
+                    "algorithmic_bytes": kbytes, "avg_launch_ms": stage_ms[kname],
+                    "other_blend_kernel": {
+                        "kernel": "blend_bwd" if kname == "blend_fwd" else "blend_fwd",
+                        "avg_launch_ms": stage_ms.get("blend_bwd" if kname == "blend_fwd"
+                                                      else "blend_fwd")}}
+        if fwd_only:
+            step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4)
+        else:
+            step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4) + H * W * (4 * D + 8) + n * (4 * D + 24)
         stats["step_hbm_frac_of_8TBps"] = step_bytes / (ms * 1e-3 / (args.steps * kviews)) / 8e12
         stats.update(alloc_stats)
         if peer is not None and peer.timing_summary() is not None:
-            stats["peer_step_ms"] = peer.timing_summary()
+            ps = peer.timing_summary()
+            stats["peer_step_ms"] = ps
+            stage_ms.pop("adam", None)
+            stage_ms["exchange_wait_slowest_rank"] = ps["barrier_in_ms"]
+            stage_ms["exchange_kernel"] = ps["kernel_ms"]
+            stage_ms["exchange_barrier_out"] = ps["barrier_out_ms"]
+
+    # ---- N > 1: one checked step (all ranks take part) -------------------------------------------
+    if world > 1 and not fwd_only and not args.no_extras:
+        chk = exchange_check(locals())
+        if rank == 0:
+            extras["exchange_check"] = chk
+
+    # ---- CUDA-class baseline: the labelled gsplat-algorithm restatement, same run ---------------
+    if rank == 0 and world == 1 and not args.no_extras and not fwd_only and cfg in (3, 4):
+        try:
+            extras["cuda_baseline"] = restatement_time(locals(), steps=3, warmup=1)
+        except Exception as e:                               # noqa: BLE001 - reported in the line
+            extras["cuda_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0 and world == 1 and not args.no_extras and fwd_only and cfg == 2:
+        try:
+            extras["cuda_baseline"] = restatement_time(locals(), steps=5, warmup=2)
+        except Exception as e:                               # noqa: BLE001
+            extras["cuda_baseline"] = {"error": f"{type(e).__name__}: {e}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import time_view
         t0 = time.time()
-        info = time_view(scene, scene.cameras[0], D, n_tiles=32)
+        info = time_view(scene, scene.cameras[0], D, n_tiles=args.cpu_tiles, backward=not fwd_only)
         cpu = {"value": info["views_per_s"], "unit": "views/s", "cores": info["cores"],
-               "kind": "port", "sample": info["sample"],
+               "kind": "port", "sample": info["sample"], "geom_s": round(info["geom_s"], 3),
+               "blend_s_extrapolated": round(info["blend_s_extrapolated"], 3),
+               "tile_ms_p10_p50_p90": info["tile_ms_p10_p50_p90"],
                "wall_s": round(time.time() - t0, 1)}
         stats["n_isects"] = info["n_isects"]
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world,
+        line = {"metric": METRICS[cfg], "value": value, "unit": "views/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"config{args.config}: N={n}, {H}x{W}, D={D}, render + fused "
-                                       "L1 vs emb[seg] target + feature backward + fused Adam "
-                                       "(frozen geometry)",
+                "config": {"workload": workload_string(cfg, n, H, W, D, fwd_only),
                            "priming_steps": priming,
                            "views_per_step_per_gpu": kviews, "parallelism": f"view-dp{world}",
                            "grad_exchange": exchange,
-                           "l2": "inputs (2 GB feature table, 2 GB raster) exceed the 126 MB L2",
-                           "optimizer_in_timed_region": True},
+                           "l2": "inputs (feature table, raster) exceed the 126 MB L2"
+                                 if n * D * 4 > 2e8 else
+                                 "views cycle over 64 cameras; feature table + raster > 126 MB L2"
+                                 if (n * D + H * W * D) * 4 > 1.3e8 else "working set fits L2: "
+                                 "consecutive views use different cameras, no flush",
+                           "optimizer_in_timed_region": not fwd_only},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "stage_ms": stage_ms, "stats": stats}
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def dense_target_leg(env):
+    """The Appendix-B contract workload beside the fused one: a dense random [H,W,D] target
+    (N(0, 0.1^2)), dense fused L1 kernel (writes the [H,W,D] gradient map) + cached feature backward
+    through autograd + Adam.  e2e copies the 2.1 GB target from pinned host memory every view."""
+    import torch
+    from gags_b200.synthetic import make_target
+    from gags_b200.utils.loss_utils import l1_loss_fused
+    H, W, D, dev, cams, pc = env["H"], env["W"], env["D"], env["dev"], env["cams"], env["pc"]
+    render_view, timed, args, n_views = env["render_view"], env["timed"], env["args"], env["n_views"]
+    tgt_host = make_target(H, W, D, 777).pin_memory()
+    tgt_dev = tgt_host.to(dev)
+    copy_stream = env["copy_stream"]
+
+    def step_dense(step):
+        pkg = render_view(cams[step % n_views])
+        loss = l1_loss_fused(pkg["render"], tgt_dev)
+        loss.backward()
+        pc.optimizer.step()
+        pc.optimizer.zero_grad(set_to_none=True)
+        return loss
+
+    def step_dense_e2e(step):
+        with torch.cuda.stream(copy_stream):
+            t = tgt_host.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main = torch.cuda.current_stream(dev)
+        t.record_stream(main)
+        pkg = render_view(cams[step % n_views])
+        main.wait_event(ready)
+        loss = l1_loss_fused(pkg["render"], t)
+        loss.backward()
+        pc.optimizer.step()
+        pc.optimizer.zero_grad(set_to_none=True)
+        return float(loss.item())
+
+    k = max(5, args.steps // 2)
+    for i in range(3):
+        step_dense(i)
+    ms_d, _, _, _ = timed(step_dense, k, 2)
+    out = {"value": k / (ms_d * 1e-3), "unit": "views/s",
+           "workload": "dense N(0,0.1^2) [H,W,D] target (SURVEY App. B), l1_loss_fused + autograd "
+                       "backward (cached weights) + fused Adam"}
+    if not args.no_e2e:
+        ke = max(3, args.steps // 4)
+        ms_e, _, _, _ = timed(step_dense_e2e, ke, 1)
+        out["e2e"] = {"value": ke / (ms_e * 1e-3), "unit": "views/s",
+                      "h2d_bytes_per_step": int(tgt_host.numel() * 4), "d2h_bytes_per_step": 4}
+    del tgt_dev
+    return out
+
+
+def restatement_time(env, steps: int, warmup: int):
+    """Time the gsplat-algorithm restatement (baseline/gsplat_restatement.py) on the same scene and
+    shape: train.py's step (render -> eager dense L1 -> backward -> torch.optim.Adam) for the
+    training configs, render() only for the forward-only ones."""
+    import torch
+    from baseline import gsplat_restatement as G
+    from gags_b200.synthetic import make_target
+    H, W, D, dev, cams, pc, bg = (env[k] for k in ("H", "W", "D", "dev", "cams", "pc", "bg"))
+    fwd_only, n_views = env["fwd_only"], env["n_views"]
+    torch.cuda.empty_cache()
+    feat = torch.nn.Parameter(pc._semantic_feature.detach().clone())
+
+    class _PC:                                                # same getters, its own feature leaf
+        get_xyz = pc.get_xyz
+        get_semantic_feature = feat
+
+        @property
+        def get_opacity(self):
+            return pc.get_opacity
+
+        @property
+        def get_scaling(self):
+            return pc.get_scaling
+
+        @property
+        def get_rotation(self):
+            return pc.get_rotation
+
+    rp = _PC()
+    opt = None if fwd_only else torch.optim.Adam([feat], lr=1e-3, eps=1e-15)
+    gt = None if fwd_only else make_target(H, W, D, 778).to(dev).permute(2, 0, 1)   # [D,H,W] view
+    mask = None if fwd_only else torch.ones(1, H, W, dtype=torch.bool, device=dev)
+
+    def step(i):
+        cam = cams[i % n_views]
+        if fwd_only:
+            with torch.no_grad():
+                return G.render(cam, rp, None, bg)["render"]
+        out = G.render(cam, rp, None, bg)["render"]
+        loss = G.l1_loss(out * mask, gt * mask)               # train.py:163
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del feat, opt, gt
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": "views/s", "ms_per_step": ms, "kind": "restatement",
+            "steps": steps,
+            "what": "gsplat-v1.4 execution plan restated with this repo's SIMT kernels "
+                    "(ceil(D/32) narrow 16x16-tile launches + torch.cat, all-four-gradient "
+                    "atomics backward per chunk, CUB global sort with host sync, eager dense L1, "
+                    "torch.optim.Adam) — NOT a gsplat measurement: gsplat is not installed"}
+
+
+def restatement_arm(args, env):
+    """`--impl restatement`: the restatement as its own bench line (single GPU)."""
+    import torch
+    rank, world = env["rank"], env["world"]
+    if rank != 0:
+        return
+    cfg, n, H, W, D = env["cfg"], env["n"], env["H"], env["W"], env["D"]
+    r = restatement_time(env, steps=args.steps, warmup=max(1, args.warmup))
+    line = {"impl": "restatement", "metric": METRICS[cfg], "value": r["value"], "unit": "views/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_string(cfg, n, H, W, D, env["fwd_only"])
+                       + " — " + r["what"]},
+            "gpu_launches": None}
+    print(json.dumps(line), flush=True)
+
+
+def exchange_check(env):
+    """One checked optimiser step at N > 1: the exchanged gradient equals the
+    single-process sum over the same G*k rendered views, the fused exchange (or NCCL + Adam) gives
+    the parameters all_reduce + FusedAdam would, and every replica is bit-identical."""
+    import torch
+    import torch.distributed as dist
+    from gags_b200 import _C, parallel, rasterization as R
+    pc, peer, world, rank, dev = env["pc"], env["peer"], env["world"], env["rank"], env["dev"]
+    cams, targets_dev, n_targets, n_views, kviews = (env[k] for k in
+                                                     ("cams", "targets_dev", "n_targets", "n_views",
+                                                      "kviews"))
+    one_view = env["one_view"]
+    p = pc._semantic_feature
+    step = 777_000
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    if peer is not None:
+        peer.synchronize()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    saved_direct = R.direct_grad_accumulation
+    # (1) single-process reference over ALL G*k views of this step, into an ordinary buffer
+    R.direct_grad_accumulation = False
+    p.grad = None
+    loss_single = 0.0
+    for q in range(world):
+        for v in parallel.views_for_rank(step, q, world, kviews, n_views):
+            loss_single += float(one_view(cams[v], targets_dev[v % n_targets]))
+    g_single = p.grad
+    p.grad = None
+    # (2) the distributed step: own views only
+    if peer is not None:
+        R.direct_grad_accumulation = True
+        peer.grad.zero_()
+        p.grad = peer.grad
+    loss_own = 0.0
+    for v in parallel.views_for_rank(step, rank, world, kviews, n_views):
+        loss_own += float(one_view(cams[v], targets_dev[v % n_targets]))
+    g_sum = p.grad.detach().clone()
+    dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+    grad_rel = rel(g_sum, g_single)
+    del g_single
+    loss_sum = parallel.sum_over_ranks(loss_own, world, dev)
+    p0 = p.detach().clone()
+    # (3) reference update: FusedAdam arithmetic on the all-reduced gradient with the pre-step moments
+    if peer is not None:
+        def full(shard):
+            parts = [torch.empty_like(shard) for _ in range(world)]
+            dist.all_gather(parts, shard.contiguous())
+            return torch.cat(parts)[:p.numel()].contiguous()
+        m_ref, v_ref = full(peer.exp_avg), full(peer.exp_avg_sq)
+        lr, (b1, b2), eps, t = peer.lr, peer.betas, peer.eps, peer.step_count + 1
+    else:
+        st = pc.optimizer.state[p]
+        grp = pc.optimizer.param_groups[0]
+        m_ref, v_ref = st["exp_avg"].detach().clone().view(-1), st["exp_avg_sq"].detach().clone().view(-1)
+        lr, (b1, b2), eps, t = grp["lr"], grp["betas"], grp["eps"], int(st["step"].item()) + 1
+    p_ref = p0.clone()
+    _C.check(_C.lib.gags_adam_step(p_ref.data_ptr(), g_sum.data_ptr(), m_ref.data_ptr(),
+                                   v_ref.data_ptr(), p_ref.numel(), float(lr), float(b1), float(b2),
+                                   float(eps), int(t), 0, _C.stream_ptr()), "gags_adam_step")
+    # (4) the product's step
+    if peer is not None:
+        peer.step()
+        peer.synchronize()
+    else:
+        parallel.allreduce_and_step(pc.optimizer, p, world)
+        pc.optimizer.zero_grad(set_to_none=True)
+    torch.cuda.synchronize(dev)
+    param_rel = rel(p.detach(), p_ref)
+    moved = rel(p.detach(), p0) > 0.0
+    # replicas identical: an order-independent 64-bit checksum of the raw bits
+    chk = p.detach().view(torch.int32).to(torch.int64).sum().reshape(1)
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    identical = all(int(c) == int(allc[0]) for c in allc)
+    R.direct_grad_accumulation = saved_direct
+    loss_ok = abs(loss_sum - loss_single) <= 1e-5 * abs(loss_single)
+    return {"grad_sum_vs_single_process_rel_err": grad_rel, "rel_err": param_rel,
+            "replicas_identical": bool(identical), "loss_sum_matches_single_process": bool(loss_ok),
+            "loss_sum": loss_sum, "loss_single_process": loss_single, "params_moved": bool(moved),
+            "views_checked": world * kviews,
+            "reference": "dist.all_reduce + gags_adam_step (FusedAdam arithmetic) on the same "
+                         "rendered gradients"}
 
 
 if __name__ == "__main__":

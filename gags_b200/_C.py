@@ -79,6 +79,7 @@ SIGNATURES = {
                                            C.c_double, C.c_double, _i32, _p]),
     "gags_set_peer_grid": (C.c_int, [_i32]),
     "gags_set_fwd_variant": (C.c_int, [_i32]),
+    "gags_set_peer_unroll": (C.c_int, [_i32]),
     "gags_adam_step_peer": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _i64, C.c_double,
                                       C.c_double, C.c_double, C.c_double, _i32, _p]),
     "gags_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double,
@@ -93,7 +94,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 if os.environ.get("GAGS_B200_FWD_VARIANT"):          # tuning / A-B switch, see include/gags_b200.h
     if lib.gags_set_fwd_variant(int(os.environ["GAGS_B200_FWD_VARIANT"])) != 0:
-        raise ValueError("GAGS_B200_FWD_VARIANT must be 2 or 3")
+        raise ValueError("GAGS_B200_FWD_VARIANT must be 2, 3, 12 or 13")
 
 
 def check(rc: int, what: str = "gags") -> None:

@@ -30,6 +30,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
 // hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
+#include <cuda.h>
+#include <cstring>
 #include "blend_tc_common.cuh"
 
 // Optional timeline instrumentation (tools/tc_timeline.py builds a second library with
@@ -64,7 +66,6 @@ struct TcCtl {
   int wcnt[4];
   int gid[2][KB];
   // v3 roles (front = scanner + alpha evaluation, chain = transmittance chain)
-  uint64_t alpha[2][4];               // front warp w -> chain warp w: alpha rows of block w written
   int lidx[2][4][KB];                 // list index of each batch entry (for last_ids), per front warp
   int nbw[2][4];                      // batch size as published by front warp w (== gcount)
   int wdone[4];                       // chain warp w: all 32 pixels finished
@@ -95,7 +96,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
              const int *__restrict__ offsets, const int *__restrict__ ids,
              float *__restrict__ render, float *__restrict__ alphas, int *__restrict__ last_ids,
              unsigned char *__restrict__ wcache, int *__restrict__ wmeta, int *__restrict__ wlist,
-             int *__restrict__ wcount) {
+             int *__restrict__ wcount, const __grid_constant__ CUtensorMap tmap_render, int use_tma) {
   using L = TcLayout<NATOM>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -133,7 +134,6 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       mbar_init(&ctl.sdone[k], 1);                 // training: the tile store has read the A stage
       mbar_init(&ctl.afull[k], 4);                 // training: pixel warps -> store warp, A tile written
       ctl.gcount[k] = 0; ctl.skip[k] = 0;
-      for (int w = 0; w < 4; ++w) mbar_init(&ctl.alpha[k][w], 1);
     }
     for (int w = 0; w < 4; ++w) ctl.wdone[w] = 0;
     ctl.done_warps = 0; ctl.skip_from = 0; ctl.any_mma = 0; ctl.term = -1;
@@ -169,7 +169,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     for (;; ++i) {
       const int st = i & 1;
       if (warp == 0) TC_STAMP(0, i, 0);
-      mbar_wait_bounded(&ctl.alpha[st][pw], (i >> 1) & 1);
+      named_bar_sync(2 + st * 4 + pw, 64);          // front warp pw has left this batch's alphas
       if (warp == 0) TC_STAMP(0, i, 1);
       const int nb = *reinterpret_cast<volatile int *>(&ctl.nbw[st][pw]);
       if (nb == 0) {
@@ -192,17 +192,19 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = z;
       } else {
-        float4 av[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          av[c] = *reinterpret_cast<const float4 *>(arow + sw128(rowoff + c * 16));
         int lastk = -1;
-#pragma unroll
+        // rolled on purpose (instruction-cache footprint, see tc3_front_alphas); round c reads the
+        // alphas parked in chunks c and c + 4 and writes its hi / lo chunks back to the same two
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          unsigned char *ph = arow + sw128(rowoff + c * 16);
+          unsigned char *pl = arow + sw128(rowoff + (c + 4) * 16);
+          const float4 a0 = *reinterpret_cast<const float4 *>(ph);
+          const float4 a1 = *reinterpret_cast<const float4 *>(pl);
           uint4 h, l;
-          tc3_chain8(av[2 * c], av[2 * c + 1], c * 8, ps, lastk, h, l);
-          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + c * 16)) = h;
-          *reinterpret_cast<uint4 *>(arow + sw128(rowoff + (c + 4) * 16)) = l;
+          tc3_chain8(a0, a1, c * 8, ps, lastk, h, l);
+          *reinterpret_cast<uint4 *>(ph) = h;
+          *reinterpret_cast<uint4 *>(pl) = l;
         }
         if (lastk >= 0) ps.last = ctl.lidx[st][pw][lastk];
       }
@@ -281,7 +283,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (warp == 4) TC_STAMP(3, i + 1, 2);
       if (nb > 0 && *reinterpret_cast<volatile int *>(&ctl.wdone[fw]) == 0)
         tc3_front_alphas(fr, pxc, pyc, sA + st * 16384 + fw * 4096, lane);
-      mbar_arrive_warp(&ctl.alpha[st][fw]);
+      named_bar_arrive(2 + st * 4 + fw, 64);        // hardware barrier: chain warp fw blocks, no polling
       if (nb == 0) break;
       sc.qhead += nb;
     }
@@ -455,35 +457,38 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       const bool do_store = chan_ok && !skipb;
       if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
       if (warp == 8) TC_STAMP(1, i, 2);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = cw * 8 + j;
-        if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
-        load_row(i, nb, skipb, row + 4, v[j]);
-      }
-      if (warp == 8) TC_STAMP(1, i, 3);
-      // the next batch's first rows are prefetched only if its list is already out: never block
-      // on it here (its publication may itself be waiting for this batch to be consumed)
       int nb2 = -1;
       bool skip2 = false;
-      const bool ahead = __all_sync(0xffffffffu,
-                                    mbar_test_wait(&ctl.list[(i + 1) & 1], ((i + 1) >> 1) & 1));
-      if (ahead) header(i + 1, nb2, skip2);
+      bool ahead = false;
+      // ONE copy of the 4-row store + refill body, run for rows [0,4) and [4,8) of this warp
+      // (rolled: instruction-cache footprint).  The refill of the second round already belongs to
+      // batch i+1 and is issued only if that batch's list is out: never block on it here (its
+      // publication may itself be waiting for this batch to be consumed).
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        int li = i, ln = nb, lrow = cw * 8 + 4;
+        bool ls = skipb;
+        if (h == 1) {
+          ahead = __all_sync(0xffffffffu,
+                             mbar_test_wait(&ctl.list[(i + 1) & 1], ((i + 1) >> 1) & 1));
+          if (ahead) header(i + 1, nb2, skip2);
+          li = i + 1; ln = nb2; lrow = cw * 8; ls = skip2;
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = cw * 8 + 4 + j;
-        if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
-        if (nb2 > 0) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
+        for (int j = 0; j < 4; ++j) {
+          const int row = cw * 8 + 4 * h + j;
+          if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
+          load_row(li, ln, ls, lrow + j, v[j]);
+        }
+        if (warp == 8 && h == 0) TC_STAMP(1, i, 3);
       }
       fence_async_smem();
       mbar_arrive_warp(&ctl.full[st]);
       if (warp == 8) TC_STAMP(1, i, 4);
       if (!ahead) {
         header(i + 1, nb2, skip2);
-        if (nb2 > 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
-        }
+        for (int j = 0; j < 4; ++j) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
       }
       nb = nb2;
       skipb = skip2;
@@ -514,6 +519,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         seen[st] = votes_now;
         if (votes < 4) {
           const int nk = (nb + 15) >> 4;
+#pragma unroll 1
           for (int ks = 0; ks < nk; ++ks) {
             // only the 14-bit start-address field (16-B units) changes between descriptors
             const uint64_t whi = w_desc0 + (uint64_t)((st * 16384 + ks * 32) >> 4);
@@ -581,47 +587,61 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) use_bg = use_bg || (ctl.bg_nonzero[k] != 0);
     const int q = warp & 3, third = warp >> 2;
-    // one item = one 128-channel block x this warp's 32 channels x 32 pixels (a 8 x 4 block)
-    for (int idx = third; idx < L::MB * 4; idx += 3) {
-      const int mb = idx >> 2, pc = idx & 3;
+    int nbox = 0;
+    // one item = one 128-channel block x this warp's 32 channels x one pixel ROW of an 8x4 block
+    // (8 pixels = 8 TMEM columns).  Rolled over the items on purpose: an 8-store body instead of
+    // the 2 x 32 unrolled stores it replaces (instruction-cache footprint, see tc3_front_alphas).
+#pragma unroll 1
+    for (int idx = third; idx < L::MB * 16; idx += 3) {
+      const int mb = idx >> 4, pc = (idx >> 2) & 3, y = idx & 3;
       const int ch = mb * 128 + q * 32 + lane;
       if (mb * 128 + q * 32 >= nch) continue;                      // warp-uniform
-      uint32_t r[32];
+      uint32_t r[8];
       if (any) {
-        tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128 + pc * 32), r);
+        tmem_ld_32x8(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128 + pc * 32 + y * 8), r);
       } else {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = 0u;
+        for (int k = 0; k < 8; ++k) r[k] = 0u;
       }
       if (use_bg) {
         const float b = ch < nch ? ctl.bgs[ch] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          r[j] = __float_as_uint(fmaf(ctl.Tfin[pc * 32 + j], b, __uint_as_float(r[j])));
+        for (int j = 0; j < 8; ++j)
+          r[j] = __float_as_uint(fmaf(ctl.Tfin[pc * 32 + y * 8 + j], b, __uint_as_float(r[j])));
+      }
+      const int xb = x0 + ((pc & 1) << 3), yy = y0 + ((pc >> 1) << 2) + y;
+      if (yy >= H || xb >= W) continue;                            // warp-uniform
+      if (use_tma) {
+        // registers -> this warp's 1 KB staging box [8 px][32 ch] -> ONE tensor store (the hardware
+        // clips the ragged right edge and channels past D); two boxes alternate so that the store
+        // of item k reads shared memory while item k+1 is staged
+        unsigned char *box = sm + warp * 2048 + (nbox & 1) * 1024;
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint32_t *>(box + x * 128 + lane * 4) = r[x];
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_render, box, ch0 + mb * 128 + q * 32, xb, yy);
+          bulk_commit_group();
+        }
+        ++nbox;
+        continue;
       }
       if (ch >= nch) continue;
-      const int xb = x0 + ((pc & 1) << 3), yb = y0 + ((pc >> 1) << 2);
-      float *dst = render + ((size_t)yb * W + xb) * D + ch0 + ch;
-      const size_t rowstride = (size_t)W * D;
-      if (xb + 8 <= W && yb + 4 <= H) {                            // interior block: no predicates
+      float *dst = render + ((size_t)yy * W + xb) * D + ch0 + ch;
+      if (xb + 8 <= W) {                                           // interior: no predicates
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-#pragma unroll
-          for (int x = 0; x < 8; ++x) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[y * 8 + x]));
-          dst += rowstride;
-        }
+        for (int x = 0; x < 8; ++x) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[x]));
       } else {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          if (yb + y < H) {
-#pragma unroll
-            for (int x = 0; x < 8; ++x)
-              if (xb + x < W) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[y * 8 + x]));
-          }
-          dst += rowstride;
-        }
+        for (int x = 0; x < 8; ++x)
+          if (xb + x < W) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[x]));
       }
     }
+    if (use_tma && lane == 0) bulk_wait_group<0>();
   }
   if (warp == 0) TC_STAMP(3, 0, 3);
   tc_fence_before();
@@ -631,6 +651,39 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 
 // 2 = one thread per pixel evaluates alpha and the chain (round-1 kernel); 3 = front / chain split.
 int g_fwd_variant = 3;
+// epilogue: 1 = TMA tensor stores from a staged box (UTMASTG), 0 = per-lane streaming stores
+int g_fwd_tma_epilogue = 1;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// tensor map of the channel-last raster [H][W][D] fp32 with a (32 channels x 8 pixels x 1 row) box
+bool make_render_map(CUtensorMap *m, float *render, int D, int W, int H) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (D & 3) || !gags_aligned16(render)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)W, (cuuint64_t)H};
+  const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)W * D * 4};
+  const cuuint32_t box[3] = {32, 8, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, render, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <int NATOM, bool V3>
 int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
@@ -645,17 +698,23 @@ int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, c
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
   }
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const int use_tma = (g_fwd_tma_epilogue && make_render_map(&tmap, render, D, W, H)) ? 1 : 0;
   blend_fwd_tc<NATOM, V3><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
       reinterpret_cast<const float4 *>(geom), colors, D, ch0, nch, bg, W, H, tw, offsets, ids,
-      render, alphas, last_ids, wcache, wmeta, wlist, wcount);
+      render, alphas, last_ids, wcache, wmeta, wlist, wcount, tmap, use_tma);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
 
 extern "C" int gags_set_fwd_variant(int32_t v) {
-  if (v != 2 && v != 3) return GAGS_EINVAL;
-  g_fwd_variant = v;
+  // 2 / 3 = role layout (see the header); + 10 = per-lane streaming stores instead of the TMA
+  // tensor-store epilogue
+  if (v != 2 && v != 3 && v != 12 && v != 13) return GAGS_EINVAL;
+  g_fwd_variant = v % 10;
+  g_fwd_tma_epilogue = v < 10 ? 1 : 0;
   return 0;
 }
 

@@ -182,29 +182,40 @@ __device__ __forceinline__ void tc_weights8(const float4 *__restrict__ rec0,
 struct TcFrontRec {
   float mx, my, A, B, C, op;
 };
+// Position (16-B chunk, before the swizzle) of alpha_k inside its pixel row: the 8 alphas the chain
+// consumes in round c (k = 8c .. 8c+7) sit exactly where that round's hi chunk (c) and lo chunk
+// (c + 4) are written afterwards, so the in-place rewrite never clobbers an alpha not yet read.
+__device__ __forceinline__ uint32_t tc3_alpha_chunk(int k) {
+  return (uint32_t)((k >> 3) + (((k >> 2) & 1) << 2));
+}
 // `rowbase` = shared address of pixel row 0 of this warp's block (rows are 128 B, block = 32 rows:
 // row y*8 + x <-> pixel (x, y) of the 8x4 block); (pxc, pyc) = centre of the block's first pixel.
+// The y loop is deliberately NOT unrolled: with five roles running side by side the kernel lives
+// or dies by its instruction-cache footprint (ncu: 60-70 % no_inst stalls when every role body was
+// fully unrolled), so each role's steady-state body is kept around 1-2 KB of SASS.
 __device__ __forceinline__ void tc3_front_alphas(const TcFrontRec &g, float pxc, float pyc,
                                                  unsigned char *rowbase, int lane) {
   float dx[8], m[8];
   uint32_t off[8];
+  const uint32_t cpos = tc3_alpha_chunk(lane);
 #pragma unroll
   for (int x = 0; x < 8; ++x) {
     dx[x] = g.mx - (pxc + (float)x);
     m[x] = g.A * dx[x];
-    off[x] = (uint32_t)x * 128u + ((uint32_t)((lane >> 2) ^ x) << 4) + ((uint32_t)(lane & 3) << 2);
+    off[x] = (uint32_t)x * 128u + ((cpos ^ (uint32_t)x) << 4) + ((uint32_t)(lane & 3) << 2);
   }
-#pragma unroll
+#pragma unroll 1
   for (int y = 0; y < 4; ++y) {
     const float dy = g.my - (pyc + (float)y);
     const float u = (g.C * dy) * dy;
+    unsigned char *rb = rowbase + y * 1024;
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
       const float t = fmaf(g.B, dy, m[x]);
       const float q = fmaf(t, dx[x], u);
       const float al = fminf(GAGS_ALPHA_MAX, g.op * tc_ex2(q));
       const float a = (q <= 0.f && al >= GAGS_ALPHA_MIN) ? al : 0.f;
-      *reinterpret_cast<float *>(rowbase + y * 1024 + off[x]) = a;
+      *reinterpret_cast<float *>(rb + off[x]) = a;
     }
   }
 }

@@ -190,14 +190,14 @@ adam_peer_kernel(PeerPtrs pp, int world, int rank, float4 *__restrict__ m, float
 // symmetric buffers.  multimem.ld_reduce returns the sum over all ranks' copies, formed inside the
 // switch, and multimem.st writes all replicas with one store, so a rank moves 1/G of the table in
 // each direction instead of (G-1)/G and the kernel is bound by HBM, not by the NVLink ports.
+template <int U>
 __global__ void __launch_bounds__(256)
 adam_multicast_kernel(const float4 *mc_grad, float4 *mc_param, const float4 *__restrict__ p_local,
                       float4 *__restrict__ m, float4 *__restrict__ v, long long start,
                       long long count, float step_size, float b1, float b2, float omb1, float omb2,
                       float inv_sqrt_bc2, float eps) {
-  // a small grid (the exchange runs beside the next view's projection / sort) with four switch
+  // a small grid (the exchange runs beside the next view's projection / sort) with U switch
   // reductions in flight per thread to cover the NVLink round trip
-  constexpr int U = 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; k0 < count; k0 += U * stride) {
     float4 g[U], pa[U], ma[U], va[U];
@@ -353,9 +353,16 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
 // Tuning hook for the two exchange kernels (tools/peer_rate.py sweeps it): CTAs per SM of their
 // grids; 0 = the built-in choice (4 for the unicast form, 2 for the multicast form).
 static int g_peer_ctas_per_sm = 0;
+static int g_peer_unroll = 4;
 extern "C" int gags_set_peer_grid(int32_t ctas_per_sm) {
   if (ctas_per_sm < 0 || ctas_per_sm > 16) return GAGS_EINVAL;
   g_peer_ctas_per_sm = ctas_per_sm;
+  return 0;
+}
+// reductions in flight per thread of the multicast form: 2, 4 (default) or 8
+extern "C" int gags_set_peer_unroll(int32_t unroll) {
+  if (unroll != 2 && unroll != 4 && unroll != 8) return GAGS_EINVAL;
+  g_peer_unroll = unroll;
   return 0;
 }
 
@@ -426,11 +433,16 @@ extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
   long long blocks = (c4 + 255) / 256;
   const long long cap_m = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
   if (blocks > cap_m) blocks = cap_m;                          // small grid, 4 reductions per thread
-  adam_multicast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),
-      reinterpret_cast<const float4 *>(param_local), reinterpret_cast<float4 *>(exp_avg_shard),
-      reinterpret_cast<float4 *>(exp_avg_sq_shard), start / 4, c4, step_size, (float)beta1,
-      (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps);
+#define GAGS_MC_LAUNCH(U)                                                                        \
+  adam_multicast_kernel<U><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                   \
+      reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),             \
+      reinterpret_cast<const float4 *>(param_local), reinterpret_cast<float4 *>(exp_avg_shard),    \
+      reinterpret_cast<float4 *>(exp_avg_sq_shard), start / 4, c4, step_size, (float)beta1,        \
+      (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps)
+  if (g_peer_unroll == 2) GAGS_MC_LAUNCH(2);
+  else if (g_peer_unroll == 8) GAGS_MC_LAUNCH(8);
+  else GAGS_MC_LAUNCH(4);
+#undef GAGS_MC_LAUNCH
   GAGS_CHECK_LAUNCH();
   return 0;
 }

@@ -121,6 +121,38 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 8 consecutive columns -> 8 registers per thread (the rolled epilogues: small bodies)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- TMA tensor store (shared -> global through a CUtensorMap, SASS: UTMASTG) ---------------------
+// 3-D tile store of the dense box at `smem_src`; out-of-bounds elements are clipped by the hardware.
+__device__ __forceinline__ void tma_store_3d(const void *tmap, const void *smem_src, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tmap)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- SWIZZLE_128B store addressing --------------------------------------------------------------
 // byte offset inside a 1024-B aligned region of 128-B rows: XOR the 16-B chunk index with row % 8
 __device__ __forceinline__ uint32_t sw128(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
@@ -137,6 +169,13 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t &hi, ui
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// non-blocking arrival on a named barrier (producer side of a bar.arrive / bar.sync hand-off: the
+// consumer blocks in hardware, no mbarrier polling).  The fence orders the producer's shared-memory
+// writes before the arrival.
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // named-barrier OR-reduction over `nthreads` threads (all of them must call it)
 __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {

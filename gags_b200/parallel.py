@@ -134,7 +134,9 @@ class PeerAdam:
         self.param = param
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.step_count = 0
-        self.timing = [] if os.environ.get("GAGS_B200_PEER_TIMING") else None   # per-step CUDA events
+        # per-step CUDA events (wait for the slowest rank / fused kernel / closing barrier): four
+        # event records per step on the exchange stream, kept for the last 64 steps
+        self.timing = None if os.environ.get("GAGS_B200_PEER_TIMING") == "0" else []
         dev = param.device
         numel = param.numel()
         self.padded, self.per = peer_slices(numel, self.world)
@@ -214,6 +216,8 @@ class PeerAdam:
             if ev:
                 ev[3].record(xs)
                 self.timing.append(ev)
+                if len(self.timing) > 64:
+                    del self.timing[:-64]
             # re-zero the persistent gradient buffer for the next backward
             C.check(C.lib.gags_zero_fill(self._buf.data_ptr() + 4 * self.padded, 4 * self.padded,
                                          xs.cuda_stream), "gags_zero_fill")
@@ -237,7 +241,7 @@ class PeerAdam:
 
     def timing_summary(self, last: int = 10):
         """Average ms of (wait for the slowest rank, fused kernel, closing barrier) over the last
-        steps; needs GAGS_B200_PEER_TIMING=1."""
+        steps (GAGS_B200_PEER_TIMING=0 switches the event records off)."""
         if not self.timing:
             return None
         torch.cuda.synchronize(self.param.device)

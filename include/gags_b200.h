@@ -275,10 +275,13 @@ int gags_adam_step_multicast(const float *mc_grad, float *mc_param, const float 
 /* Tuning hook: CTAs per SM of the two exchange kernels' grids (0 = built-in: 4 unicast, 2
  * multicast).  Process-wide; used by tools/peer_rate.py.                                         */
 int gags_set_peer_grid(int32_t ctas_per_sm);
+/* Tuning hook: switch reductions in flight per thread of the multicast exchange (2, 4 or 8).      */
+int gags_set_peer_unroll(int32_t unroll);
 
 /* Tuning hook: wide forward blend variant.  3 (default) = alpha evaluation (lane = Gaussian) and
  * transmittance chain (lane = pixel) in two warp groups; 2 = one thread per pixel does both (the
- * round-1 kernel).  Bit-identical outputs; process-wide; used by the parity tests and bench.      */
+ * round-1 kernel); add 10 (12 / 13) for per-lane streaming stores instead of the TMA tensor-store
+ * epilogue.  Bit-identical outputs; process-wide; used by the parity tests and bench.             */
 int gags_set_fwd_variant(int32_t variant);
 
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream

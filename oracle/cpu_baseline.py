@@ -16,7 +16,8 @@ import torch
 from . import gags_oracle as O
 
 
-def time_view(scene, cam, D: int, n_tiles: int = 48, seed: int = 0, threads: int | None = None):
+def time_view(scene, cam, D: int, n_tiles: int = 256, seed: int = 0, threads: int | None = None,
+              backward: bool = True):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     W, H = int(cam.image_width), int(cam.image_height)
@@ -35,7 +36,9 @@ def time_view(scene, cam, D: int, n_tiles: int = 48, seed: int = 0, threads: int
     feats = scene.semantic_feature[:, :D]
     op = opac.squeeze(-1)
     t1 = time.perf_counter()
+    per_tile = []
     for t in sample:
+        tt = time.perf_counter()
         s, e = o2[t], o2[t + 1]
         if e <= s:
             continue
@@ -48,12 +51,17 @@ def time_view(scene, cam, D: int, n_tiles: int = 48, seed: int = 0, threads: int
         w, keep, t_fin = O._tile_weights(px, m2d[sel], con[sel], op[sel])
         f = feats[sel]
         out = w @ f                                   # forward blend
-        v_out = torch.sign(out)                       # dL1/dout
-        _ = w.T @ v_out                               # feature backward
+        if backward:
+            v_out = torch.sign(out)                   # dL1/dout
+            _ = w.T @ v_out                           # feature backward
+        per_tile.append((time.perf_counter() - tt) * 1e3)
     t_blend = (time.perf_counter() - t1) * (tw * th) / max(1, len(sample))
+    pt = sorted(per_tile) or [0.0]
+    spread = [round(pt[int(q * (len(pt) - 1))], 3) for q in (0.1, 0.5, 0.9)]
     total = t_geom + t_blend
     return dict(seconds_per_view=total, views_per_s=1.0 / total, geom_s=t_geom,
-                blend_s_extrapolated=t_blend, cores=threads,
-                sample=f"projection+keys+sort on all N={scene.xyz.shape[0]}; blend fwd+bwd_feat on "
-                       f"{len(sample)} of {tw * th} tiles, extrapolated",
+                blend_s_extrapolated=t_blend, cores=threads, tile_ms_p10_p50_p90=spread,
+                sample=f"projection+keys+sort on all N={scene.xyz.shape[0]}; blend "
+                       f"{'fwd+bwd_feat' if backward else 'fwd'} on {len(sample)} of {tw * th} "
+                       "tiles, extrapolated",
                 n_isects=int(keys.numel()), n_visible=int((radii > 0).sum()))

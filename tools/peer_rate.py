@@ -3,8 +3,7 @@
 all-reduce + Adam + all-gather kernel alone on a config-3 sized table for both forms (unicast P2P /
 NVLS multimem) and several grid sizes, and prints GB/s per direction per rank.
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/peer_rate.py
-Written when the round's multi-GPU budget was spent: not run yet (the hook it drives,
-gags_set_peer_grid, defaults to the measured grids)."""
+Drives the tuning hooks gags_set_peer_grid / gags_set_peer_unroll."""
 import os
 import sys
 
@@ -30,18 +29,22 @@ for form in ("0", "1"):
         continue
     # bytes per direction per rank
     per_dir = gb * (1 + 1 / world) if peer.multicast else gb * 2 * (world - 1) / world
-    for ctas in (1, 2, 4, 8):
-        _C.check(_C.lib.gags_set_peer_grid(ctas))
-        peer.timing.clear()
-        for _ in range(6):
-            peer.step()
-            peer.synchronize()
-        t = peer.timing_summary(last=4)
-        if rank == 0:
-            print(f"{'NVLS   ' if peer.multicast else 'unicast'} {world} ranks, {ctas} CTAs/SM: kernel "
-                  f"{t['kernel_ms']:.3f} ms = {per_dir / t['kernel_ms'] * 1e3:.0f} GB/s per direction "
-                  f"(barriers {t['barrier_in_ms']:.3f} + {t['barrier_out_ms']:.3f} ms)", flush=True)
+    for unroll in ((2, 4, 8) if peer.multicast else (4,)):
+        _C.check(_C.lib.gags_set_peer_unroll(unroll))
+        for ctas in (1, 2, 4, 8):
+            _C.check(_C.lib.gags_set_peer_grid(ctas))
+            peer.timing.clear()
+            for _ in range(6):
+                peer.step()
+                peer.synchronize()
+            t = peer.timing_summary(last=4)
+            if rank == 0:
+                print(f"{'NVLS   ' if peer.multicast else 'unicast'} {world} ranks, {ctas} CTAs/SM, "
+                      f"{unroll} in flight: kernel {t['kernel_ms']:.3f} ms = "
+                      f"{per_dir / t['kernel_ms'] * 1e3:.0f} GB/s per direction "
+                      f"(barriers {t['barrier_in_ms']:.3f} + {t['barrier_out_ms']:.3f} ms)", flush=True)
     _C.check(_C.lib.gags_set_peer_grid(0))
+    _C.check(_C.lib.gags_set_peer_unroll(4))
     del peer, p
     torch.cuda.synchronize()
     dist.barrier()
