@@ -62,6 +62,7 @@ SIGNATURES = {
     "gags_blend_fwd": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "gags_blend_bwd_features": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "gags_blend_cache_supported": (C.c_int, [_i32]),
+    "gags_blend_last_ids_optional": (C.c_int, [_i32]),
     "gags_blend_cache_slots": (_i64, [_i64, _i32]),
     "gags_blend_fwd_cached": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                         _p, _p]),
@@ -72,6 +73,9 @@ SIGNATURES = {
                                       _p, _p, _p]),
     "gags_l1_loss_fused": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p]),
     "gags_l1_loss_segmap": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _f, _p, _p, _p]),
+    "gags_l1_loss_sam": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _f, _p, _p, _p, _p]),
+    "gags_blend_bwd_features_cached_sam": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                                                     _p, _i32, _f, _p, _p, _p, _p]),
     "gags_scale_inplace": (C.c_int, [_p, _p, _i64, _p]),
     "gags_memset_zero": (C.c_int, [_p, _sz, _p]),
     "gags_zero_fill": (C.c_int, [_p, _i64, _p]),

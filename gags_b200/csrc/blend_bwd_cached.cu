@@ -102,6 +102,10 @@ __device__ __forceinline__ CbJob cb_job(long long j, int nblk, int tile_w, int c
 // emb[seg]| into *loss — the semantics of l1_loss_segmap_kernel (train_ops.cu), without the 2 GB
 // gradient map ever existing in HBM.  Every (pixel, channel) is staged by exactly one job, half
 // tiles without Gaussians included (they only contribute to the loss).
+// LM = 3: the reference's full target (read_sam_clip_feature, scene/dataset_readers.py:54-121):
+// `seg` holds three levels [3][H*W], `scale3` the per-pixel level weights [3][H*W], the target row is
+// sum_l scale3[l] * emb[seg[l]], a pixel is valid when all three ids are, and (optionally) the
+// gradient w.r.t. the level weights is accumulated into v_scale [3][H*W] (see l1_loss_sam_kernel).
 struct CbL1 {
   const int *seg;
   const float *emb;
@@ -109,9 +113,12 @@ struct CbL1 {
   float *loss;
   int n_seg;
   float scale;
+  const float *scale3;
+  float *v_scale;
+  long long hw;
 };
 
-template <bool L1>
+template <int LM>
 __global__ void __launch_bounds__(CB_THREADS, 2)
 blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, long long njobs,
                  const int *__restrict__ offsets, const unsigned char *__restrict__ wcache,
@@ -119,6 +126,8 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
                  const int *__restrict__ wcount, int *__restrict__ jobctr,
                  const float *__restrict__ v_render, float *__restrict__ v_colors, CbL1 l1) {
   using L = CbLayout;
+  constexpr bool L1 = LM != 0;
+  constexpr int NL = LM == 3 ? 3 : 1;               // target levels
   // The kernel has no static shared memory, so the dynamic window starts at the CTA's shared-memory
   // base (1 KB aligned, which SWIZZLE_128B needs); the layout uses every byte of the two-CTAs-per-SM
   // budget, so this is checked instead of padded.
@@ -183,15 +192,19 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
       const bool chan_ok = n0 < jb.cvalid;
       const float *vbase = v_render + jb.cfirst + n0;
       // pixels per round: the fused-loss form also holds the target rows, so it takes half as many
-      constexpr int PJ = L1 ? 4 : 8;
-      int sg_cur[PJ];
+      constexpr int PJ = LM == 3 ? 2 : (L1 ? 4 : 8);
+      int sg_cur[PJ][NL];
       auto load_seg = [&](int round) {
 #pragma unroll
         for (int jj = 0; jj < PJ; ++jj) {
           const int ql = 2 * (round * PJ + jj) + (lane >> 4);
           const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
-          sg_cur[jj] = -1;
-          if (L1 && chan_ok && xx < W && yy < H) sg_cur[jj] = __ldg(l1.seg + (size_t)yy * W + xx);
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            sg_cur[jj][l] = -1;
+            if (L1 && chan_ok && xx < W && yy < H)
+              sg_cur[jj][l] = __ldg(l1.seg + (size_t)l * l1.hw + (size_t)yy * W + xx);
+          }
         }
       };
       if constexpr (L1) load_seg(0);
@@ -202,34 +215,43 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
         if constexpr (L1) {
           // the segment ids of this round were loaded one round ahead (sg_cur): the target row's
           // address depends on them, and a load chain seg -> emb per round showed up as +0.1 ms
-          int sg[PJ];
-          float mk[PJ];
+          int sg[PJ][NL];
+          float mk[PJ], wl[PJ][NL];
 #pragma unroll
           for (int jj = 0; jj < PJ; ++jj) {
             const int ql = 2 * (round * PJ + jj) + (lane >> 4);
             const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
-            sg[jj] = sg_cur[jj];
             mk[jj] = 0.f;
-            if (chan_ok && xx < W && yy < H)
-              mk[jj] = l1.mask ? fabsf(__ldg(l1.mask + (size_t)yy * W + xx)) : 1.f;
+            const bool in = chan_ok && xx < W && yy < H;
+            if (in) mk[jj] = l1.mask ? fabsf(__ldg(l1.mask + (size_t)yy * W + xx)) : 1.f;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+              sg[jj][l] = sg_cur[jj][l];
+              wl[jj][l] = 1.f;
+              if (LM == 3 && in) wl[jj][l] = __ldg(l1.scale3 + (size_t)l * l1.hw + (size_t)yy * W + xx);
+              if (sg[jj][l] < 0 || sg[jj][l] >= l1.n_seg) mk[jj] = 0.f;   // no target: weight 0
+            }
           }
-          float4 t[PJ][2];
+          float4 t[PJ][NL][2];
 #pragma unroll
           for (int jj = 0; jj < PJ; ++jj) {
             const int ql = 2 * (round * PJ + jj) + (lane >> 4);
             const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
-            v[jj][0] = v[jj][1] = t[jj][0] = t[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[jj][0] = v[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) t[jj][l][0] = t[jj][l][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (chan_ok && xx < W && yy < H) {
               const float4 *src = reinterpret_cast<const float4 *>(vbase + ((size_t)yy * W + xx) * D);
               v[jj][0] = ldg_nc4(src);
               v[jj][1] = ldg_nc4(src + 1);
-              if (sg[jj] >= 0 && sg[jj] < l1.n_seg) {
-                const float4 *te =
-                    reinterpret_cast<const float4 *>(l1.emb + (size_t)sg[jj] * D + jb.cfirst + n0);
-                t[jj][0] = __ldg(te);
-                t[jj][1] = __ldg(te + 1);
-              } else {
-                mk[jj] = 0.f;                          // no target for this pixel: weight 0
+              if (mk[jj] != 0.f) {
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                  const float4 *te = reinterpret_cast<const float4 *>(
+                      l1.emb + (size_t)sg[jj][l] * D + jb.cfirst + n0);
+                  t[jj][l][0] = __ldg(te);
+                  t[jj][l][1] = __ldg(te + 1);
+                }
               }
             }
           }
@@ -238,16 +260,40 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
           for (int jj = 0; jj < PJ; ++jj) {
             const float sc = l1.scale * mk[jj];
             float part = 0.f;
-#define GAGS_L1C(h, c)                                              \
-            {                                                       \
-              const float d = v[jj][h].c - t[jj][h].c;              \
-              part += fabsf(d);                                     \
-              v[jj][h].c = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);    \
+            float vs[NL];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) vs[l] = 0.f;
+#define GAGS_L1C(h, c)                                                                         \
+            {                                                                                  \
+              float tg = t[jj][0][h].c;                                                        \
+              if (LM == 3)   /* same order as l1_loss_sam_kernel: ((w0 e0) + w1 e1) + w2 e2 */    \
+                tg = fmaf(wl[jj][NL - 1], t[jj][NL - 1][h].c,                                   \
+                          fmaf(wl[jj][1 % NL], t[jj][1 % NL][h].c, wl[jj][0] * tg));            \
+              const float d = v[jj][h].c - tg;                                                 \
+              part += fabsf(d);                                                                \
+              const float gq = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);                           \
+              v[jj][h].c = gq;                                                                 \
+              if (LM == 3) {                                                                   \
+                _Pragma("unroll") for (int l = 0; l < NL; ++l)                                 \
+                    vs[l] = fmaf(-gq, t[jj][l][h].c, vs[l]);                                   \
+              }                                                                                \
             }
             GAGS_L1C(0, x) GAGS_L1C(0, y) GAGS_L1C(0, z) GAGS_L1C(0, w)
             GAGS_L1C(1, x) GAGS_L1C(1, y) GAGS_L1C(1, z) GAGS_L1C(1, w)
 #undef GAGS_L1C
             l1acc = fmaf(mk[jj], part, l1acc);
+            if (LM == 3 && l1.v_scale != nullptr) {
+              // this lane's 8 channels -> the 16 lanes that share the pixel -> one atomic per level
+              const int ql = 2 * (round * PJ + jj) + (lane >> 4);
+              const int xx = jb.x0 + ((q & 1) << 3) + (ql & 7), yy = jb.y0 + ((q >> 1) << 2) + (ql >> 3);
+#pragma unroll
+              for (int l = 0; l < NL; ++l) {
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) vs[l] += __shfl_xor_sync(0xffffffffu, vs[l], o);
+                if ((lane & 15) == 0 && mk[jj] != 0.f && xx < W && yy < H)
+                  atomicAdd(l1.v_scale + (size_t)l * l1.hw + (size_t)yy * W + xx, vs[l]);
+              }
+            }
           }
           if (!live) continue;                         // empty half tile: loss only
         } else {
@@ -412,7 +458,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
   if (warp == 9) tmem_dealloc<L::TCOLS>(tb);
 }
 
-template <bool L1>
+template <int LM>
 int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const unsigned char *wcache,
               const int *wmeta, const int *wlist, int *wcount, const float *v_render,
               float *v_colors, CbL1 l1, cudaStream_t st) {
@@ -421,7 +467,7 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   const int hh = (H + 7) / 8;
   const int nblk = (nch + 127) / 128;
   {   // per-device attribute: set on every launch (a process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<L1>,
+    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<LM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
   }
@@ -432,7 +478,7 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
   cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
-  blend_bwd_cached<L1><<<grid, CB_THREADS, L::BYTES, st>>>(
+  blend_bwd_cached<LM><<<grid, CB_THREADS, L::BYTES, st>>>(
       D, ch0, nch, nblk, W, H, tw, njobs, offsets, wcache, wmeta, wlist, wcount, jobctr, v_render,
       v_colors, l1);
   return (int)cudaGetLastError();
@@ -453,7 +499,7 @@ extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t 
   const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = launch_cb<false>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
+    const int rc = launch_cb<0>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
                                     v_render, v_colors, CbL1{}, st);
     if (rc != 0) return rc;
   }
@@ -479,11 +525,43 @@ extern "C" int gags_blend_bwd_features_cached_l1(int32_t D, int32_t width, int32
     return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
-  const CbL1 l1{seg, emb, mask, loss_out, n_seg, grad_scale};
+  const CbL1 l1{seg, emb, mask, loss_out, n_seg, grad_scale, nullptr, nullptr, 0};
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = launch_cb<true>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
-                                   render, v_colors, l1, st);
+    const int rc = launch_cb<1>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
+                                render, v_colors, l1, st);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// The same with the reference's full three-level target (CbL1, LM = 3; semantics of
+// gags_l1_loss_sam): seg3 [3][H*W], scale_map3 [3][H*W], optional v_scale_map [3][H*W] (zeroed by the
+// caller).
+extern "C" int gags_blend_bwd_features_cached_sam(int32_t D, int32_t width, int32_t height,
+                                                  const int32_t *offsets, const void *wcache,
+                                                  const int32_t *wmeta, const int32_t *wlist,
+                                                  int32_t *wcount, const float *render,
+                                                  const int32_t *seg3, const float *emb,
+                                                  const float *scale_map3, int32_t n_seg,
+                                                  float grad_scale, float *loss_out,
+                                                  float *v_scale_map, float *v_colors,
+                                                  void *stream) {
+  if (!offsets || !wcache || !wmeta || !wlist || !wcount || !render || !v_colors || !seg3 || !emb ||
+      !scale_map3 || !loss_out)
+    return GAGS_EINVAL;
+  if (D <= 32 || D % 16 != 0 || width <= 0 || height <= 0 || n_seg < 1) return GAGS_EINVAL;
+  if (!gags_aligned16(wcache) || !gags_aligned16(render) || !gags_aligned16(v_colors) ||
+      !gags_aligned16(emb))
+    return GAGS_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char *wc = reinterpret_cast<const unsigned char *>(wcache);
+  const CbL1 l1{seg3, emb, nullptr, loss_out, n_seg, grad_scale, scale_map3, v_scale_map,
+                (long long)width * height};
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const int rc = launch_cb<3>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
+                                render, v_colors, l1, st);
     if (rc != 0) return rc;
   }
   return 0;

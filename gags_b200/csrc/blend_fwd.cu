@@ -318,17 +318,20 @@ int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const f
                       unsigned char *wcache, int32_t *wmeta, int32_t *wlist, int32_t *wcount,
                       cudaStream_t st);
 extern int g_gags_blend_impl;
+extern "C" int gags_blend_last_ids_optional(int32_t D);
 
 static int blend_fwd_impl(const float *geom, const float *colors, int32_t D, const float *background,
                           int32_t width, int32_t height, const int32_t *offsets,
                           const int32_t *flatten_ids, float *render, float *alphas,
                           int32_t *last_ids, unsigned char *wcache, int32_t *wmeta, int32_t *wlist,
                           int32_t *wcount, void *stream) {
-  if (!geom || !colors || !offsets || !render || !alphas || !last_ids) return GAGS_EINVAL;
+  if (!geom || !colors || !offsets || !render || !alphas) return GAGS_EINVAL;
   if (D < 1 || width <= 0 || height <= 0) return GAGS_EINVAL;
   if (!gags_aligned16(geom)) return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = D > 32 && D % 16 == 0 && g_gags_blend_impl != 1;
+  // last_ids may be NULL only where the kernel has a path that does not track it
+  if (!last_ids && !gags_blend_last_ids_optional(D)) return GAGS_EINVAL;
   if (wcache && !tc) return GAGS_EINVAL;
   if (D <= 32) {
     if (D <= 4) return launch_narrow<4>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
@@ -364,6 +367,11 @@ extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
                               float *alphas, int32_t *last_ids, void *stream) {
   return blend_fwd_impl(geom, colors, D, background, width, height, offsets, flatten_ids, render,
                         alphas, last_ids, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern int g_fwd_variant;
+extern "C" int gags_blend_last_ids_optional(int32_t D) {
+  return (D > 32 && D % 16 == 0 && g_gags_blend_impl != 1 && g_fwd_variant == 3) ? 1 : 0;
 }
 
 extern "C" int gags_blend_cache_supported(int32_t D) {

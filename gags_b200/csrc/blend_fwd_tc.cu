@@ -50,6 +50,9 @@ extern "C" int gags_debug_timeline(long long *host_dst, int n) {
 #define TC_STAMP(role, batch, ev) do { } while (0)
 #endif
 
+// 2 = one thread per pixel evaluates alpha and the chain (round-1 kernel); 3 = front / chain split.
+int g_fwd_variant = 3;
+
 namespace {
 
 constexpr int KB = TC_KB;
@@ -148,6 +151,20 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     if (lane == 0) ctl.bg_nonzero[warp] = nzw ? 1 : 0;
   }
   if (warp == 12) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  // v3: the front warps start walking the tile list right away — the first scan round is two
+  // dependent global loads (ids -> geometry) of pure latency, and nothing it touches (the survivor
+  // ring, named barrier 1) depends on the barrier / TMEM set-up the other warps are doing
+  TcScanner sc;
+  if (V3 && warp >= 4 && warp < 8) {
+    sc.init(geom, ids, s, e, (float)x0 + 0.5f, (float)y0 + 0.5f, rg0, rg1, rgid, ctl.wcnt,
+            tid - 128);
+    if (sc.scan < e) sc.issue();
+    while (sc.queued() < KB && sc.more()) {
+      if (!sc.pending) sc.issue();
+      sc.finish();
+    }
+    if (!sc.pending && sc.queued() < 2 * KB && sc.scan < e) sc.issue();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -161,8 +178,10 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
     const int pxi = x0 + dx, pyi = y0 + dy;
     const bool inside = (pxi < W) && (pyi < H);
+    // last_ids == NULL selects the FAST chain (see tc3_chain8): T then accumulates sum w
+    const bool want_last = last_ids != nullptr;
     TcChain ps;
-    ps.P = inside ? 1.f : 0.f; ps.T = 1.f; ps.last = 0;
+    ps.P = inside ? 1.f : 0.f; ps.T = want_last ? 1.f : 0.f; ps.last = 0;
     bool counted = false;
     const uint32_t rowoff = (uint32_t)tid * 128u;
     int i = 0;
@@ -202,11 +221,12 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
           const float4 a0 = *reinterpret_cast<const float4 *>(ph);
           const float4 a1 = *reinterpret_cast<const float4 *>(pl);
           uint4 h, l;
-          tc3_chain8(a0, a1, c * 8, ps, lastk, h, l);
+          if (want_last) tc3_chain8<false>(a0, a1, c * 8, ps, lastk, h, l);
+          else tc3_chain8<true>(a0, a1, c * 8, ps, lastk, h, l);
           *reinterpret_cast<uint4 *>(ph) = h;
           *reinterpret_cast<uint4 *>(pl) = l;
         }
-        if (lastk >= 0) ps.last = ctl.lidx[st][pw][lastk];
+        if (want_last && lastk >= 0) ps.last = ctl.lidx[st][pw][lastk];
       }
       if (warp == 0) TC_STAMP(0, i, 2);
       fence_async_smem();
@@ -223,22 +243,18 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         }
       }
     }
-    ctl.Tfin[tid] = ps.T;
+    ctl.Tfin[tid] = want_last ? ps.T : 1.f - ps.T;
     if (inside && ch0 == 0) {
       const size_t pix = (size_t)pyi * W + pxi;
-      alphas[pix] = 1.f - ps.T;
-      last_ids[pix] = ps.last;
+      alphas[pix] = want_last ? 1.f - ps.T : ps.T;
+      if (want_last) last_ids[pix] = ps.last;
     }
     if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
   } else if (V3 && warp < 8) {
     // ======================= v3 front warps: scanner + alpha evaluation ============================
     // lane = Gaussian of the batch: the record stays in registers and the warp evaluates the 32
     // alphas of ITS 8x4 pixel block (front warp w <-> chain warp w), all independent
-    const int p = tid - 128;
     const int fw = warp - 4;
-    TcScanner sc;
-    sc.init(geom, ids, s, e, (float)x0 + 0.5f, (float)y0 + 0.5f, rg0, rg1, rgid, ctl.wcnt, p);
-    if (sc.scan < e) sc.issue();
     const float pxc = (float)(x0 + ((fw & 1) << 3)) + 0.5f;
     const float pyc = (float)(y0 + ((fw >> 1) << 2)) + 0.5f;
     for (int i = 0;; ++i) {
@@ -587,58 +603,63 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) use_bg = use_bg || (ctl.bg_nonzero[k] != 0);
     const int q = warp & 3, third = warp >> 2;
+    // one item = one 128-channel block x this warp's 32 channels x one 8x4 pixel block: a single
+    // tcgen05.ld (32 lanes x 32 columns), 32 conflict-free shared-memory stores into the warp's
+    // [4 rows][8 px][32 ch] staging box and ONE tensor store (UTMASTG; the hardware clips the ragged
+    // right / bottom edges and channels past D).  The main loop's A / B stages are dead by now and
+    // hold the boxes; with 256 channels there is room for two per warp, so the store of item k
+    // reads shared memory while item k+1 is staged.  (Per-lane streaming stores — 32 per item —
+    // kept the LSU queue full for ~10 k cycles per CTA; so did 8-column items, by sheer count.)
+    constexpr int NBUF = (L::B_OFF + 4 * L::BPART >= 12 * 8192) ? 2 : 1;
+    unsigned char *boxes = sm + warp * (4096 * NBUF);
     int nbox = 0;
-    // one item = one 128-channel block x this warp's 32 channels x one pixel ROW of an 8x4 block
-    // (8 pixels = 8 TMEM columns).  Rolled over the items on purpose: an 8-store body instead of
-    // the 2 x 32 unrolled stores it replaces (instruction-cache footprint, see tc3_front_alphas).
 #pragma unroll 1
-    for (int idx = third; idx < L::MB * 16; idx += 3) {
-      const int mb = idx >> 4, pc = (idx >> 2) & 3, y = idx & 3;
+    for (int idx = third; idx < L::MB * 4; idx += 3) {
+      const int mb = idx >> 2, pc = idx & 3;
       const int ch = mb * 128 + q * 32 + lane;
       if (mb * 128 + q * 32 >= nch) continue;                      // warp-uniform
-      uint32_t r[8];
+      const int xb = x0 + ((pc & 1) << 3), yb = y0 + ((pc >> 1) << 2);
+      if (yb >= H || xb >= W) continue;                            // warp-uniform
+      uint32_t r[32];
       if (any) {
-        tmem_ld_32x8(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128 + pc * 32 + y * 8), r);
+        tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128 + pc * 32), r);
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = 0u;
+        for (int k = 0; k < 32; ++k) r[k] = 0u;
       }
       if (use_bg) {
         const float b = ch < nch ? ctl.bgs[ch] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          r[j] = __float_as_uint(fmaf(ctl.Tfin[pc * 32 + y * 8 + j], b, __uint_as_float(r[j])));
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(fmaf(ctl.Tfin[pc * 32 + j], b, __uint_as_float(r[j])));
       }
-      const int xb = x0 + ((pc & 1) << 3), yy = y0 + ((pc >> 1) << 2) + y;
-      if (yy >= H || xb >= W) continue;                            // warp-uniform
       if (use_tma) {
-        // registers -> this warp's 1 KB staging box [8 px][32 ch] -> ONE tensor store (the hardware
-        // clips the ragged right edge and channels past D); two boxes alternate so that the store
-        // of item k reads shared memory while item k+1 is staged
-        unsigned char *box = sm + warp * 2048 + (nbox & 1) * 1024;
-        if (lane == 0) bulk_wait_group_read<1>();
+        unsigned char *box = boxes + (NBUF == 2 ? (nbox & 1) * 4096 : 0);
+        if (lane == 0) bulk_wait_group_read<NBUF - 1>();
         __syncwarp();
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          *reinterpret_cast<uint32_t *>(box + x * 128 + lane * 4) = r[x];
+        for (int j = 0; j < 32; ++j)
+          *reinterpret_cast<uint32_t *>(box + j * 128 + lane * 4) = r[j];
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmap_render, box, ch0 + mb * 128 + q * 32, xb, yy);
+          tma_store_3d(&tmap_render, box, ch0 + mb * 128 + q * 32, xb, yb);
           bulk_commit_group();
         }
         ++nbox;
         continue;
       }
       if (ch >= nch) continue;
-      float *dst = render + ((size_t)yy * W + xb) * D + ch0 + ch;
-      if (xb + 8 <= W) {                                           // interior: no predicates
+      float *dst = render + ((size_t)yb * W + xb) * D + ch0 + ch;
+      const size_t rowstride = (size_t)W * D;
 #pragma unroll
-        for (int x = 0; x < 8; ++x) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[x]));
-      } else {
+      for (int y = 0; y < 4; ++y) {
+        if (yb + y < H) {
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          if (xb + x < W) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[x]));
+          for (int x = 0; x < 8; ++x)
+            if (xb + x < W) stg_cs1(dst + (unsigned)(x * D), __uint_as_float(r[y * 8 + x]));
+        }
+        dst += rowstride;
       }
     }
     if (use_tma && lane == 0) bulk_wait_group<0>();
@@ -649,8 +670,6 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   if (warp == 12) tmem_dealloc<L::TCOLS>(tb);
 }
 
-// 2 = one thread per pixel evaluates alpha and the chain (round-1 kernel); 3 = front / chain split.
-int g_fwd_variant = 3;
 // epilogue: 1 = TMA tensor stores from a staged box (UTMASTG), 0 = per-lane streaming stores
 int g_fwd_tma_epilogue = 1;
 
@@ -672,13 +691,13 @@ EncodeTiledFn encode_tiled_fn() {
   }
   return fn;
 }
-// tensor map of the channel-last raster [H][W][D] fp32 with a (32 channels x 8 pixels x 1 row) box
+// tensor map of the channel-last raster [H][W][D] fp32 with a (32 channels x 8 pixels x 4 rows) box
 bool make_render_map(CUtensorMap *m, float *render, int D, int W, int H) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || (D & 3) || !gags_aligned16(render)) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)W, (cuuint64_t)H};
   const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)W * D * 4};
-  const cuuint32_t box[3] = {32, 8, 1};
+  const cuuint32_t box[3] = {32, 8, 4};
   const cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, render, dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -221,11 +221,21 @@ __device__ __forceinline__ void tc3_front_alphas(const TcFrontRec &g, float pxc,
 }
 
 struct TcChain {
-  float P, T;
+  float P, T;   // EXACT: T = transmittance frozen at the stop.  FAST: T accumulates sum_k w_k.
   int last;
 };
-// 8 consecutive alphas of the batch (positions k0 .. k0+7) at one pixel -> bf16 hi / lo chunks;
-// `lastk` receives the in-batch position of the last contributor (unchanged when there is none).
+// 8 consecutive alphas of the batch (positions k0 .. k0+7) at one pixel -> bf16 hi / lo chunks.
+// EXACT (the caller wants last_ids, i.e. the full geometry backward may follow): the same compare /
+// select chain as tc_weights8, bit-identical to it; `lastk` receives the in-batch position of the
+// last contributor (unchanged when there is none).
+// FAST (frozen-geometry training and inference, where nobody reads last_ids): ncu showed the ALU
+// pipe (compares, selects, integer ops: half rate) as the kernel's busiest unit, and 6 of the
+// chain's 12 instructions per Gaussian sat on it.  Here the "pixel still alive" mask is formed on
+// the FMA pipe, s = saturate((P' - 1e-4) * 2^60): the product is exact, so s is exactly 1 or 0, and
+// w = (alpha * P) * s is bit-identical to the select it replaces; the final transmittance is
+// recovered as 1 - sum_k w_k (one more FADD per Gaussian) instead of a select per step, which
+// changes render_alpha by a few 1e-7 (it is mathematically the same quantity).
+template <bool FAST>
 __device__ __forceinline__ void tc3_chain8(const float4 &a0, const float4 &a1, int k0, TcChain &st,
                                            int &lastk, uint4 &hi, uint4 &lo) {
   const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -234,18 +244,30 @@ __device__ __forceinline__ void tc3_chain8(const float4 &a0, const float4 &a1, i
 #pragma unroll
   for (int k = 0; k < 8; ++k) P[k + 1] = fmaf(-a[k], P[k], P[k]);
   float w[8];
-  float T = st.T;
-  int lk = lastk;
+  if (FAST) {
+    constexpr float BIG = 1152921504606846976.f;          // 2^60
+    float sum = st.T;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const bool alive = P[k + 1] > GAGS_T_STOP;
-    w[k] = alive ? a[k] * P[k] : 0.f;
-    T = alive ? P[k + 1] : T;
-    lk = (w[k] > 0.f) ? (k0 + k) : lk;
+    for (int k = 0; k < 8; ++k) {
+      const float s = __saturatef(fmaf(P[k + 1], BIG, -GAGS_T_STOP * BIG));
+      w[k] = (a[k] * P[k]) * s;
+      sum += w[k];
+    }
+    st.T = sum;
+  } else {
+    float T = st.T;
+    int lk = lastk;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool alive = P[k + 1] > GAGS_T_STOP;
+      w[k] = alive ? a[k] * P[k] : 0.f;
+      T = alive ? P[k + 1] : T;
+      lk = (w[k] > 0.f) ? (k0 + k) : lk;
+    }
+    st.T = T;
+    lastk = lk;
   }
   st.P = P[8];
-  st.T = T;
-  lastk = lk;
   split_pack2(w[0], w[1], hi.x, lo.x);
   split_pack2(w[2], w[3], hi.y, lo.y);
   split_pack2(w[4], w[5], hi.z, lo.z);

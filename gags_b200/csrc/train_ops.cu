@@ -107,6 +107,82 @@ l1_loss_segmap_kernel(const float4 *__restrict__ r, const int *__restrict__ seg,
   }
 }
 
+// The reference's real target (read_sam_clip_feature, /root/reference/scene/dataset_readers.py:54-121,
+// default mode, called at /root/reference/train.py:162-166): three SAM levels (s, m, l) of segment ids
+// per pixel, one embedding table, and a per-pixel weight per level (the scale decoder's softmax):
+//     gt[px, :] = sum_l scale[l, px] * emb[seg[l, px], :]        valid(px) = all three seg != -1
+//     loss = mean(|render * valid - gt * valid|)                  (utils/loss_utils.py:20-21)
+// (the reference's bilinear resize of the three maps is the identity when the scale map has the
+// image's size, which is how train.py runs it; other sizes take the dense fallback in Python).
+// One pass: loss, v_render = scale * valid * sign(render - gt) and, when requested, the gradient
+// w.r.t. the scale map, v_scale[l, px] = -sum_ch v_render[px, ch] * emb[seg[l, px], ch], which is what
+// trains the scale decoder through the target (train.py:149 -> :162).
+template <bool VS>
+__global__ void __launch_bounds__(256)
+l1_loss_sam_kernel(const float4 *__restrict__ r, const int *__restrict__ seg3,
+                   const float4 *__restrict__ emb, const float *__restrict__ scale3, long long hw,
+                   long long n4, int d4, int n_seg, float scale, float *__restrict__ loss,
+                   float4 *__restrict__ vout, float *__restrict__ v_scale) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // with VS the host guarantees d4 % 32 == 0: a warp's 32 float4 belong to ONE pixel
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_nc4(r + i);
+    const long long pix = i / d4;
+    const int c4 = (int)(i - pix * d4);
+    int sg[3];
+    float w[3];
+    bool ok = true;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      sg[l] = __ldg(seg3 + l * hw + pix);
+      w[l] = __ldg(scale3 + l * hw + pix);
+      ok = ok && sg[l] >= 0 && sg[l] < n_seg;
+    }
+    float4 e[3];
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      e[l] = ok ? __ldg(emb + (size_t)sg[l] * d4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t.x = fmaf(w[l], e[l].x, t.x); t.y = fmaf(w[l], e[l].y, t.y);
+      t.z = fmaf(w[l], e[l].z, t.z); t.w = fmaf(w[l], e[l].w, t.w);
+    }
+    const float m = ok ? 1.f : 0.f;
+    const float dx = a.x - t.x, dy = a.y - t.y, dz = a.z - t.z, dw = a.w - t.w;
+    acc += m * (fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw));
+    const float s = scale * m;
+    float4 g;
+    g.x = dx > 0.f ? s : (dx < 0.f ? -s : 0.f);
+    g.y = dy > 0.f ? s : (dy < 0.f ? -s : 0.f);
+    g.z = dz > 0.f ? s : (dz < 0.f ? -s : 0.f);
+    g.w = dw > 0.f ? s : (dw < 0.f ? -s : 0.f);
+    vout[i] = g;
+    if (VS) {
+      float vs[3];
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        vs[l] = -(g.x * e[l].x + g.y * e[l].y + g.z * e[l].z + g.w * e[l].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vs[l] += __shfl_xor_sync(0xffffffffu, vs[l], o);
+      }
+      if ((threadIdx.x & 31) == 0 && ok) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) atomicAdd(v_scale + l * hw + pix, vs[l]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_part[w];
+    atomicAdd(loss, v);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
             float4 *__restrict__ v, long long n4, float step_size, float b1, float b2,
@@ -311,6 +387,34 @@ extern "C" int gags_l1_loss_segmap(const float *render, const int32_t *seg, cons
   l1_loss_segmap_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(render), seg, reinterpret_cast<const float4 *>(emb), mask, n4,
       D / 4, n_seg, grad_scale, loss_out, reinterpret_cast<float4 *>(v_render));
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+// v_scale_map (optional, [3][HW], zeroed by the caller) needs D % 128 == 0 (a warp per pixel slice).
+extern "C" int gags_l1_loss_sam(const float *render, const int32_t *seg3, const float *emb,
+                                const float *scale_map3, int64_t HW, int32_t D, int32_t n_seg,
+                                float grad_scale, float *loss_out, float *v_render,
+                                float *v_scale_map, void *stream) {
+  if (!render || !seg3 || !emb || !scale_map3 || !loss_out || !v_render || HW < 0 || D < 1 || n_seg < 1)
+    return GAGS_EINVAL;
+  if (D % 4 != 0) return GAGS_EINVAL;
+  if (v_scale_map && D % 128 != 0) return GAGS_ERANGE;
+  if (!gags_aligned16(render) || !gags_aligned16(emb) || !gags_aligned16(v_render)) return GAGS_EALIGN;
+  if (HW == 0) return 0;
+  const long long n4 = (long long)HW * (D / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > gags_sm_count() * 8) blocks = gags_sm_count() * 8;
+  if (v_scale_map)
+    l1_loss_sam_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(render), seg3, reinterpret_cast<const float4 *>(emb),
+        scale_map3, HW, n4, D / 4, n_seg, grad_scale, loss_out,
+        reinterpret_cast<float4 *>(v_render), v_scale_map);
+  else
+    l1_loss_sam_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(render), seg3, reinterpret_cast<const float4 *>(emb),
+        scale_map3, HW, n4, D / 4, n_seg, grad_scale, loss_out,
+        reinterpret_cast<float4 *>(v_render), nullptr);
   GAGS_CHECK_LAUNCH();
   return 0;
 }

@@ -32,6 +32,11 @@ TILE = 16
 # (parallel.allreduce_grads does not use hooks).
 direct_grad_accumulation = False
 
+# last_ids (index of the last contributor per pixel) is read by the full geometry backward only.
+# When no geometry gradient is needed the wide forward skips tracking it (cheaper transmittance
+# chain, see csrc/blend_tc_common.cuh tc3_chain8) and info["last_ids"] is None; set this to keep it.
+want_last_ids = False
+
 # Keep the forward's blend-weight tiles for the feature backward (training with frozen geometry).
 # The parity tests switch it off to exercise the recomputing backward kernels as well.
 weight_cache = True
@@ -503,6 +508,37 @@ class _FusedHandle:
 _last_cached_ctx = None
 
 
+def _fused_handle(render_dhw):
+    """(handle, channel-last render) when `render_dhw` is the output of a forward that kept its
+    weight tiles and has not been consumed yet, else (None, None)."""
+    h = getattr(render_dhw, "_gags_fused", None)
+    r = render_dhw.permute(1, 2, 0) if render_dhw.dim() == 3 else None
+    if (h is not None and h.ctx.lease is not None and r is not None and r.is_contiguous()
+            and r.data_ptr() == h.render_ptr):
+        return h, r
+    return None, None
+
+
+def _finish_fused_backward(render_dhw, h, v_colors, sink) -> None:
+    """Hand the feature gradient of a fused loss + backward call to its owner."""
+    ctx = h.ctx
+    ctx.lease = None               # this view's weight tiles are spent: back to the pool
+    render_dhw._gags_fused = None
+    if sink is not None:
+        if sink.grad is None:
+            sink.grad = v_colors
+    elif h.cols.requires_grad:
+        cols = h.cols
+        if cols.is_leaf:
+            # what AccumulateGrad does with a gradient nobody else holds: adopt it (no 2 GB copy)
+            if cols.grad is None:
+                cols.grad = v_colors
+            else:
+                cols.grad.add_(v_colors)
+        else:
+            torch.autograd.backward([cols], [v_colors])  # through whatever produced the features
+
+
 def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
     """loss = mean(|render - emb[seg]| * mask) AND its backward into the feature table in one
     kernel: equivalent to `loss = l1_loss_segmap_fused(render, seg, emb, mask); loss.backward()`
@@ -511,13 +547,9 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
     written nor read.  `render_dhw` must be the tensor render() / rasterize_view() returned for a
     forward that kept its weight tiles (frozen geometry, trainable features); anything else falls
     back to the two-kernel form.  Returns the detached loss."""
-    from .utils.loss_utils import l1_loss_segmap_fused
-    h = getattr(render_dhw, "_gags_fused", None)
-    r = render_dhw.permute(1, 2, 0) if render_dhw.dim() == 3 else None
-    ok = (h is not None and h.ctx.lease is not None and r is not None and r.is_contiguous()
-          and r.data_ptr() == h.render_ptr and seg_hw.dtype == torch.int32
-          and emb.dtype == torch.float32 and emb.dim() == 2)
-    if not ok:
+    from .utils.loss_utils import _mask_f32, l1_loss_segmap_fused
+    h, r = _fused_handle(render_dhw)
+    if h is None or seg_hw.dtype != torch.int32 or emb.dtype != torch.float32 or emb.dim() != 2:
         loss = l1_loss_segmap_fused(render_dhw, seg_hw, emb, mask_hw)
         loss.backward()
         return loss.detach()
@@ -525,13 +557,10 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
     width, height, D, N = ctx.dims
     if seg_hw.shape != (height, width) or emb.shape[1] != D:
         raise ValueError("seg must be int32 [H,W] and emb float32 [n_seg, D]")
-    _C.require_cuda(seg_hw, emb)
+    _C.require_cuda(seg_hw, emb, mask_hw)
     dev = r.device
     sg, em = seg_hw.contiguous(), emb.contiguous()
-    from .utils.loss_utils import _mask_f32
-    _C.require_cuda(mask_hw)
     m = _mask_f32(mask_hw, height, width)
-    need_col = h.cols.requires_grad
     _mark("bwd_start")
     v_colors, sink = _take_grad_buffer(ctx, True, False, N, D, dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -544,23 +573,51 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
         _C.ptr(loss), _C.ptr(v_colors), _C.stream_ptr()), "gags_blend_bwd_features_cached_l1")
     _C.count_launch((D + 255) // 256)
     _mark("blend_bwd")
-    # this view's weight tiles are spent: hand the buffers back before the next forward
-    ctx.lease = None
-    render_dhw._gags_fused = None
-    if sink is not None:
-        if sink.grad is None:
-            sink.grad = v_colors
-    elif need_col:
-        cols = h.cols
-        if cols.is_leaf:
-            # what AccumulateGrad does with a gradient nobody else holds: adopt it (no 2 GB copy)
-            if cols.grad is None:
-                cols.grad = v_colors
-            else:
-                cols.grad.add_(v_colors)
-        else:
-            torch.autograd.backward([cols], [v_colors])  # through whatever produced the features
+    _finish_fused_backward(render_dhw, h, v_colors, sink)
     return loss[0] / numel
+
+
+def fused_sam_backward(render_dhw, seg3, emb, scale_map, want_scale_grad: bool = False):
+    """The same single-kernel loss + backward against the reference's FULL distillation target
+    (read_sam_clip_feature + l1_loss, /root/reference/scene/dataset_readers.py:54-121 and
+    /root/reference/train.py:162-163): `seg3` int32 [3,H,W] (SAM levels s, m, l; -1 = none), `emb`
+    [n_seg, D], `scale_map` float32 [3,H,W] (the scale decoder's output).  Returns (loss,
+    d loss / d scale_map or None).  Falls back to loss_utils.l1_loss_sam_fused + backward when the
+    render did not keep its weight tiles."""
+    from .utils.loss_utils import l1_loss_sam_fused
+    h, r = _fused_handle(render_dhw)
+    ok = (h is not None and seg3.dtype == torch.int32 and seg3.dim() == 3 and seg3.shape[0] == 3
+          and emb.dtype == torch.float32 and emb.dim() == 2
+          and scale_map.dtype == torch.float32 and scale_map.shape == seg3.shape)
+    if ok:
+        width, height, D, N = h.ctx.dims
+        ok = tuple(seg3.shape[1:]) == (height, width) and emb.shape[1] == D \
+            and not (want_scale_grad and D % 128 != 0)
+    if not ok:
+        sm = scale_map.detach().requires_grad_(True) if want_scale_grad else scale_map
+        loss = l1_loss_sam_fused(render_dhw, seg3, emb, sm)
+        loss.backward()
+        return loss.detach(), (sm.grad if want_scale_grad else None)
+    ctx = h.ctx
+    _C.require_cuda(seg3, emb, scale_map)
+    dev = r.device
+    sg, em, sc = seg3.contiguous(), emb.contiguous(), scale_map.detach().contiguous()
+    v_scale = torch.zeros_like(sc) if want_scale_grad else None
+    _mark("bwd_start")
+    v_colors, sink = _take_grad_buffer(ctx, True, False, N, D, dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    _mark("bwd_zero")
+    cache = ctx.lease.bufs
+    numel = float(height * width * D)
+    _C.check(_C.lib.gags_blend_bwd_features_cached_sam(
+        D, width, height, _C.ptr(h.offsets), _C.ptr(cache[0]), _C.ptr(cache[1]), _C.ptr(cache[2]),
+        _C.ptr(cache[3]), _C.ptr(r), _C.ptr(sg), _C.ptr(em), _C.ptr(sc), em.shape[0], 1.0 / numel,
+        _C.ptr(loss), _C.ptr(v_scale), _C.ptr(v_colors), _C.stream_ptr()),
+        "gags_blend_bwd_features_cached_sam")
+    _C.count_launch((D + 255) // 256)
+    _mark("blend_bwd")
+    _finish_fused_backward(render_dhw, h, v_colors, sink)
+    return loss[0] / numel, v_scale
 
 
 class _Blend(torch.autograd.Function):
@@ -587,10 +644,12 @@ class _Blend(torch.autograd.Function):
         bg = _f32c(background) if background is not None else None
         render = torch.empty(height, width, D, dtype=torch.float32, device=dev)
         alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
-        last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
         # frozen geometry + trainable features (the shipped training loop): keep the blend-weight
         # tiles of this forward so the backward is a streaming GEMM instead of a second tile walk
         need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        last_ids = None
+        if need_geo or want_last_ids or not _C.lib.gags_blend_last_ids_optional(D):
+            last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
         cache = None
         if (weight_cache and ctx.needs_input_grad[3] and not need_geo
                 and _C.lib.gags_blend_cache_supported(D)):
@@ -623,7 +682,8 @@ class _Blend(torch.autograd.Function):
         global _last_cached_ctx
         _last_cached_ctx = ctx if cache is not None else None
         ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
-        ctx.mark_non_differentiable(last_ids)
+        if last_ids is not None:
+            ctx.mark_non_differentiable(last_ids)
         return render, alphas, last_ids
 
     @staticmethod

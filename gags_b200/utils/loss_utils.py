@@ -97,6 +97,83 @@ def l1_loss_segmap_fused(render_dhw, seg_hw, emb, mask_hw=None):
     return _L1Fused.apply(render_dhw.permute(1, 2, 0), None, mask_hw, seg_hw, emb)
 
 
+class _L1Sam(torch.autograd.Function):
+    """loss of train.py:162-163 against read_sam_clip_feature's default-mode target, one pass."""
+
+    @staticmethod
+    def forward(ctx, render_hwd, seg3, emb, scale_map):
+        _C.require_cuda(render_hwd, seg3, emb, scale_map)
+        r = render_hwd.contiguous()
+        H, W, D = r.shape
+        if seg3.dtype != torch.int32 or tuple(seg3.shape) != (3, H, W):
+            raise ValueError("seg3 must be int32 [3,H,W] (use sam_levels() on the reference's seg_map)")
+        if emb.dim() != 2 or emb.shape[1] != D or emb.dtype != torch.float32:
+            raise ValueError("img_embed must be float32 [n_seg, D]")
+        if tuple(scale_map.shape) != (3, H, W) or scale_map.dtype != torch.float32:
+            raise ValueError("scale_map must be float32 [3,H,W] at the render's size")
+        want_vs = ctx.needs_input_grad[3]
+        if want_vs and D % 128 != 0:
+            raise ValueError("the gradient w.r.t. scale_map needs D % 128 == 0 on the fused path")
+        sg, em, sc = seg3.contiguous(), emb.contiguous(), scale_map.contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=r.device)
+        v = torch.empty_like(r)
+        vs = torch.zeros_like(sc) if want_vs else None
+        numel = float(H * W * D)
+        _C.check(_C.lib.gags_l1_loss_sam(_C.ptr(r), _C.ptr(sg), _C.ptr(em), _C.ptr(sc), H * W, D,
+                                         em.shape[0], 1.0 / numel, _C.ptr(loss), _C.ptr(v),
+                                         _C.ptr(vs), _C.stream_ptr()), "gags_l1_loss_sam")
+        _C.count_launch()
+        ctx.save_for_backward(v, vs)
+        return loss[0] / numel
+
+    @staticmethod
+    def backward(ctx, g):
+        v, vs = ctx.saved_tensors
+        gs = g.detach().reshape(1).to(torch.float32).contiguous()
+        _C.check(_C.lib.gags_scale_inplace(_C.ptr(v), _C.ptr(gs), v.numel(), _C.stream_ptr()),
+                 "gags_scale_inplace")
+        _C.count_launch()
+        return v, None, None, (vs * gs if vs is not None else None)
+
+
+def sam_levels(seg_map: torch.Tensor) -> torch.Tensor:
+    """The reference's per-view `seg_map` ([4,h,w], level 0 unused by the target: levels 1..3 = s, m, l,
+    scene/dataset_readers.py:64-66) or an already-sliced [3,h,w] map -> contiguous int32 [3,h,w]."""
+    if seg_map.dim() != 3 or seg_map.shape[0] not in (3, 4):
+        raise ValueError("seg_map must be [4,h,w] or [3,h,w]")
+    s = seg_map[1:4] if seg_map.shape[0] == 4 else seg_map
+    return s.to(torch.int32).contiguous()
+
+
+def l1_loss_sam_fused(render_dhw, seg_map, img_embed, scale_map):
+    """`gt, m = read_sam_clip_feature(img_embed, seg_map, scale_map); l1_loss(render * m, gt * m)`
+    (train.py:162-163, default mode) in one pass that never materialises `gt`: the kernel gathers
+    the three levels' embeddings, weights them with `scale_map` and masks pixels where any level is
+    -1.  Gradients flow to the render and (D % 128 == 0) to `scale_map`.  When the maps are not at the
+    render's size the reference's resize is needed: the dense route below is taken instead."""
+    D, H, W = render_dhw.shape
+    seg3 = seg_map if (seg_map.dtype == torch.int32 and seg_map.shape[0] == 3
+                       and seg_map.is_contiguous()) else sam_levels(seg_map)
+    if tuple(seg3.shape[1:]) != (H, W) or tuple(scale_map.shape[1:]) != (H, W) or \
+            (scale_map.requires_grad and D % 128 != 0):
+        from ..scene.dataset_readers import read_sam_clip_feature
+        full = seg_map if seg_map.shape[0] == 4 else torch.cat([seg_map[:1], seg_map])
+        gt, m = read_sam_clip_feature(img_embed, full, scale_map)
+        if scale_map.requires_grad:
+            return l1_loss(render_dhw * m, gt * m)
+        return l1_loss_fused(render_dhw, gt.permute(1, 2, 0).contiguous(), m)
+    return _L1Sam.apply(render_dhw.permute(1, 2, 0), seg3, img_embed, scale_map)
+
+
+def l1_backward_fused_sam(render_dhw, seg_map, img_embed, scale_map, want_scale_grad=False):
+    """l1_loss_sam_fused + backward as ONE kernel inside the cached feature backward
+    (rasterization.fused_sam_backward); returns (detached loss, d loss / d scale_map or None)."""
+    from ..rasterization import fused_sam_backward
+    seg3 = seg_map if (seg_map.dtype == torch.int32 and seg_map.shape[0] == 3
+                       and seg_map.is_contiguous()) else sam_levels(seg_map)
+    return fused_sam_backward(render_dhw, seg3, img_embed, scale_map, want_scale_grad)
+
+
 def l1_backward_fused(render_dhw, seg_hw, emb, mask_hw=None):
     """`loss = l1_loss_segmap_fused(...); loss.backward()` as ONE call that never materialises the
     [H,W,D] loss gradient (rasterization.fused_l1_backward); returns the detached loss."""

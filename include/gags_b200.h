@@ -185,7 +185,12 @@ int gags_blend_bwd_features(const float *geom, int32_t D, int32_t width, int32_t
  * n_tiles)`:  wcache[slots * 16384] bytes (16-B aligned), wmeta[slots * 32], wlist[slots],
  * wcount[tile_w * ceil(height / 8) + 1] (the extra int is the backward's job counter).  None needs
  * initialising.                                                                                */
-int gags_blend_cache_supported(int32_t D);     /* 1 if the cached pair handles this D          */
+int gags_blend_cache_supported(int32_t D);
+/* 1 when gags_blend_fwd / gags_blend_fwd_cached accept last_ids == NULL for this D (the wide
+ * tensor-core kernel then skips the last-contributor tracking and the per-step selects of the
+ * transmittance chain; render_alphas = sum of the blend weights instead of 1 - T, equal to a few
+ * 1e-7).  last_ids is only read by gags_blend_bwd_full.                                           */
+int gags_blend_last_ids_optional(int32_t D);     /* 1 if the cached pair handles this D          */
 int64_t gags_blend_cache_slots(int64_t n_isects, int32_t n_tiles);
 int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
                           const float *background, int32_t width, int32_t height,
@@ -236,6 +241,26 @@ int gags_l1_loss_fused(const float *render, const float *target, const float *ma
 int gags_l1_loss_segmap(const float *render, const int32_t *seg, const float *emb,
                         const float *mask, int64_t HW, int32_t D, int32_t n_seg, float grad_scale,
                         float *loss_out, float *v_render, void *stream);
+
+/* The same loss against the reference's FULL target (read_sam_clip_feature, default mode,
+ * /root/reference/scene/dataset_readers.py:54-121 called at /root/reference/train.py:162-166): three
+ * SAM levels of segment ids seg3[3][HW] (-1 = none), one table emb[n_seg, D] and the per-pixel level
+ * weights scale_map3[3][HW] (the scale decoder's output at image size):
+ *   target[p,:] = sum_l scale_map3[l,p] * emb[seg3[l,p],:],  valid(p) = all three ids in [0, n_seg).
+ * v_scale_map (optional, [3][HW], zeroed by the caller, needs D % 128 == 0) receives d loss /
+ * d scale_map3 — the path through which train.py trains the scale decoder (:149 -> :162).        */
+int gags_l1_loss_sam(const float *render, const int32_t *seg3, const float *emb,
+                     const float *scale_map3, int64_t HW, int32_t D, int32_t n_seg,
+                     float grad_scale, float *loss_out, float *v_render, float *v_scale_map,
+                     void *stream);
+/* ... and fused into the cached feature backward (cf. gags_blend_bwd_features_cached_l1).        */
+int gags_blend_bwd_features_cached_sam(int32_t D, int32_t width, int32_t height,
+                                       const int32_t *offsets, const void *wcache,
+                                       const int32_t *wmeta, const int32_t *wlist, int32_t *wcount,
+                                       const float *render, const int32_t *seg3, const float *emb,
+                                       const float *scale_map3, int32_t n_seg, float grad_scale,
+                                       float *loss_out, float *v_scale_map, float *v_colors,
+                                       void *stream);
 
 /* v[0..numel) *= *scale_dev (a DEVICE scalar), a no-op pass when the scalar is exactly 1: chains the
  * fused loss's stored gradient with autograd's incoming grad_output without a host sync and, in the

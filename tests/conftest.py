@@ -16,3 +16,13 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_utils.npz"))
+
+
+@pytest.fixture
+def want_last_ids():
+    """Keep last_ids in the wide forward (otherwise skipped when no geometry gradient is needed)."""
+    from gags_b200 import rasterization as R
+    old = R.want_last_ids
+    R.want_last_ids = True
+    yield
+    R.want_last_ids = old

@@ -136,3 +136,25 @@ def test_loss_utils_match_reference_formulas():
     assert l1_loss_map(a, b).shape == (5, 4)
     assert torch.isclose(l2_loss(a, b), ((a - b) ** 2).mean())
     assert torch.isclose(cos_loss(a, b), 1 - torch.nn.functional.cosine_similarity(a, b, 0).mean())
+
+
+def test_read_sam_clip_feature_dense_route_matches_restatement():
+    """gags_b200.scene.dataset_readers.read_sam_clip_feature (the product's dense route / fallback)
+    against the statement-by-statement restatement of /root/reference/scene/dataset_readers.py:54-121
+    in oracle/sam_target.py: default and max_mode, equal-size and resized maps."""
+    import torch
+    from gags_b200.scene.dataset_readers import read_sam_clip_feature as mine
+    from oracle.sam_target import read_sam_clip_feature as ref
+    g = torch.Generator().manual_seed(0)
+    H, W, D, S = 20, 28, 16, 7
+    seg = torch.randint(-1, S, (4, H, W), generator=g).float()
+    emb = torch.randn(S, D, generator=g)
+    for hs, ws in ((H, W), (40, 56)):
+        scale = torch.softmax(torch.randn(3, hs, ws, generator=g), 0)
+        for mm in (False, True):
+            a, ma = ref(emb, seg, scale, max_mode=mm)
+            b, mb = mine(emb, seg, scale, max_mode=mm)
+            assert a.shape == (D, hs, ws) and ma.shape == (1, hs, ws) and mb.dtype == torch.bool
+            assert torch.equal(ma, mb) and float((a - b).abs().max()) < 1e-6
+    fm, m = mine(emb, seg, torch.softmax(torch.randn(3, H, W, generator=g), 0), median_mode=True)
+    assert fm.shape == (D, H, W) and m.shape == (1, H, W)

@@ -154,7 +154,7 @@ def _blend_ref(st, colors, bg, W, H, dtype=torch.float64):
 
 
 @pytest.mark.parametrize("D", [3, 4, 16, 32, 64, 128, 192, 256, 512])
-def test_blend_forward_matches_oracle(D):
+def test_blend_forward_matches_oracle(D, want_last_ids):
     from gags_b200 import rasterization as R
     W, H = 112, 72                                              # ragged: 72 = 4.5 tiles
     sc = front_scene(1500, W, H, D, seed=D, sigma_px=(1.0, 8.0))
@@ -184,7 +184,7 @@ def blend_impl():
 
 @pytest.mark.parametrize("D,n,opac_lo", [(48, 1500, 0.05), (64, 1500, 0.05), (128, 6000, 0.5),
                                          (192, 1500, 0.05), (256, 6000, 0.5), (512, 1500, 0.05)])
-def test_tensor_core_forward_matches_simt_and_oracle(D, n, opac_lo, blend_impl):
+def test_tensor_core_forward_matches_simt_and_oracle(D, n, opac_lo, blend_impl, want_last_ids):
     """tcgen05 path (bf16 hi/lo split, 3 products) vs the fp32 SIMT kernel and the fp64 oracle.
     The dense cases (n = 6000, opaque) run many batches per tile and terminate early."""
     from gags_b200 import rasterization as R

@@ -277,7 +277,7 @@ def test_cached_backward_multi_job_steady_state(fused_loss):
 
 
 @pytest.mark.parametrize("train", [False, True])
-def test_forward_variants_are_bit_identical(train):
+def test_forward_variants_are_bit_identical(train, want_last_ids):
     """the v3 forward (alpha evaluation and transmittance chain in separate warp groups) performs
     the same operations in the same order as the one-thread-per-pixel kernel: identical bits in
     render / alpha / last_ids, and identical cached weight tiles (same feature gradient)."""
@@ -312,6 +312,44 @@ def test_forward_variants_are_bit_identical(train):
     assert torch.equal(r2, r3) and torch.equal(a2, a3) and torch.equal(l2, l3)
     if train:
         assert rel_err(g3, g2) < 5e-6        # atomics order differs, the weights do not
+
+
+@pytest.mark.parametrize("D", [64, 256, 512])
+def test_fast_chain_equals_exact_chain(D):
+    """Without last_ids the wide forward forms the 'pixel alive' mask on the FMA pipe and recovers
+    the transmittance as 1 - sum w: same render bits, render_alpha equal to ~1e-6, same cached
+    weights (same feature gradient); info["last_ids"] is then None."""
+    from gags_b200 import rasterization as R
+    W, H = 200, 136
+    sc = front_scene(9000, W, H, D, seed=14, sigma_px=(1.0, 10.0))
+    sc["opacities"] = sc["opacities"].clamp_min(0.3)             # many pixels saturate (T <= 1e-4)
+    dev = torch.device("cuda:0")
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    K = sc["K"]
+    gen = torch.Generator().manual_seed(6)
+    v_out = torch.randn(H, W, D, generator=gen).to(dev)
+    outs = []
+    old = R.want_last_ids
+    try:
+        for keep in (True, False):
+            R.want_last_ids = keep
+            col = torch.nn.Parameter(g["colors"].clone())
+            render, alphas, info = R.rasterize_view(
+                g["means"], g["quats"], g["scales"], g["opacities"], col, g["viewmat"],
+                float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), W, H,
+                background=torch.full((D,), 0.25, device=dev))
+            assert (info["last_ids"] is not None) == keep
+            (render * v_out).sum().backward()
+            torch.cuda.synchronize()
+            outs.append((render.detach().clone(), alphas.detach().clone(), col.grad.clone()))
+    finally:
+        R.want_last_ids = old
+    (r0, a0, g0), (r1, a1, g1) = outs
+    assert float((a0 > 0.9998).float().mean()) > 0.05            # the saturated case is exercised
+    assert float((a1 - a0).abs().max()) < 2e-6
+    # the background term T * bg inherits the 1e-7-level difference in T; the blend itself is equal
+    assert float((r1 - r0).abs().max()) <= 0.25 * 2e-6 + 1e-7
+    assert rel_err(g1, g0) < 5e-6
 
 
 def test_render_with_reference_shaped_camera_and_minicam():
@@ -377,3 +415,91 @@ def test_fused_l1_accepts_bool_mask_like_the_reference():
         l1_loss_fused(r.permute(2, 0, 1), t, mb[:, :-1])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         l1_loss_fused(r.permute(2, 0, 1), t, mb.cpu())
+
+
+def _sam_inputs(H, W, D, S, seed, hs=None, ws=None):
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.randint(-1, S, (4, H, W), generator=g).float()           # the reference stores floats
+    seg[2, : H // 5] = -1                                                # a band without level m
+    emb = torch.randn(S, D, generator=g)
+    emb = emb / emb.norm(dim=-1, keepdim=True)
+    scale = torch.softmax(2.0 * torch.randn(3, hs or H, ws or W, generator=g), dim=0)
+    return seg, emb, scale
+
+
+@pytest.mark.parametrize("H,W,D", [(37, 53, 128), (40, 64, 256), (33, 47, 48)])
+def test_sam_target_loss_matches_reference_restatement(H, W, D):
+    """l1_loss_sam_fused == read_sam_clip_feature + l1_loss(feature * mask, gt * mask)
+    (/root/reference/scene/dataset_readers.py:54-121, /root/reference/train.py:162-163): loss,
+    gradient w.r.t. the render and w.r.t. the scale map (the scale decoder's training signal)."""
+    from gags_b200.utils.loss_utils import l1_loss_sam_fused
+    from oracle.sam_target import distill_loss
+    seg, emb, scale = _sam_inputs(H, W, D, 9, seed=H)
+    g = torch.Generator().manual_seed(1)
+    r = 0.3 * torch.randn(D, H, W, generator=g)
+    a = r.cuda().requires_grad_(True)
+    sa = scale.cuda().requires_grad_(True)
+    la = l1_loss_sam_fused(a, seg.cuda(), emb.cuda(), sa)
+    (2.0 * la).backward()
+    b = r.double().requires_grad_(True)
+    sb = scale.double().requires_grad_(True)
+    lb = distill_loss(b, emb.double(), seg, sb)
+    (2.0 * lb).backward()
+    assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb))
+    assert rel_err(a.grad, b.grad) < 1e-6
+    assert rel_err(sa.grad, sb.grad) < 1e-4
+
+
+def test_sam_target_resized_maps_take_the_dense_route():
+    """maps smaller than the render: the reference's bilinear / nearest resize applies."""
+    from gags_b200.utils.loss_utils import l1_loss_sam_fused
+    from oracle.sam_target import distill_loss
+    H, W, D = 40, 56, 64
+    seg, emb, scale = _sam_inputs(20, 28, D, 7, seed=3, hs=H, ws=W)
+    g = torch.Generator().manual_seed(2)
+    r = 0.3 * torch.randn(D, H, W, generator=g)
+    a = r.cuda().requires_grad_(True)
+    la = l1_loss_sam_fused(a, seg.cuda(), emb.cuda(), scale.cuda())
+    la.backward()
+    b = r.double().requires_grad_(True)
+    lb = distill_loss(b, emb.double(), seg, scale.double())
+    lb.backward()
+    assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb))
+    assert frac_bad(a.grad, b.grad, 1e-6) < 1e-4        # sign() at fp32-vs-fp64 ties of the resize
+
+
+@pytest.mark.parametrize("D,want_vs", [(128, True), (256, True), (64, False)])
+def test_fused_sam_backward_equals_loss_then_backward(D, want_vs):
+    """l1_backward_fused_sam (three-level target formed inside the cached feature backward) ==
+    l1_loss_sam_fused + loss.backward(): loss, feature gradient, scale-map gradient."""
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_backward_fused_sam, l1_loss_sam_fused, sam_levels
+    dev = torch.device("cuda:0")
+    H, W = 75, 131
+    scene = make_scene(3000, H, W, D, seed=11, n_views=4, sigma_px_median=1.5)
+    seg, emb, scale = _sam_inputs(H, W, D, 13, seed=5)
+    seg3 = sam_levels(seg.to(dev))
+    emb, scale = (0.2 * emb).to(dev), scale.to(dev)
+    bg = torch.zeros(3, device=dev)
+    res = []
+    for fused in (False, True):
+        pc = _model(scene, dev)
+        pkg = render(scene.cameras[1].to(dev), pc, None, bg)
+        if fused:
+            assert getattr(pkg["render"], "_gags_fused", None) is not None
+            loss, vs = l1_backward_fused_sam(pkg["render"], seg3, emb, scale, want_scale_grad=want_vs)
+        else:
+            sm = scale.clone().requires_grad_(want_vs)
+            loss = l1_loss_sam_fused(pkg["render"], seg3, emb, sm)
+            loss.backward()
+            vs = sm.grad
+        torch.cuda.synchronize()
+        res.append((float(loss), pc._semantic_feature.grad.clone(), vs))
+    (l0, g0, v0), (l1, g1, v1) = res
+    assert abs(l0 - l1) < 1e-5 * abs(l0)
+    assert float(g0.abs().max()) > 0 and rel_err(g1, g0) < 2e-6
+    if want_vs:
+        assert rel_err(v1, v0) < 1e-5
+    else:
+        assert v1 is None
