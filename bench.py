@@ -200,7 +200,7 @@ def main():
 
     n, H, W, D = CONFIGS[cfg]
     rgb = D == 3
-    scene = config_scene(cfg, with_sh=rgb)
+    scene = config_scene(cfg, with_sh=rgb, feature_device=dev)
     if args.n:
         n = args.n
         for f in ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest",
@@ -531,6 +531,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import time_view
+        if scene.semantic_feature.is_cuda:               # config 5: only the sampled tiles' rows matter
+            scene.semantic_feature = scene.semantic_feature.cpu()
         t0 = time.time()
         info = time_view(scene, scene.cameras[0], D, n_tiles=args.cpu_tiles, backward=not fwd_only)
         cpu = {"value": info["views_per_s"], "unit": "views/s", "cores": info["cores"],

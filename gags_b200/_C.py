@@ -76,6 +76,8 @@ SIGNATURES = {
     "gags_l1_loss_sam": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _f, _p, _p, _p, _p]),
     "gags_blend_bwd_features_cached_sam": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                                      _p, _i32, _f, _p, _p, _p, _p]),
+    "gags_pixel_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i32, _p, _p, _p]),
+    "gags_pixel_loss_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p]),
     "gags_scale_inplace": (C.c_int, [_p, _p, _i64, _p]),
     "gags_memset_zero": (C.c_int, [_p, _sz, _p]),
     "gags_zero_fill": (C.c_int, [_p, _i64, _p]),
@@ -96,6 +98,13 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+for _env, _fn in (("GAGS_B200_PEER_GRID", "gags_set_peer_grid"),
+                  ("GAGS_B200_PEER_UNROLL", "gags_set_peer_unroll")):
+    if os.environ.get(_env) and getattr(lib, _fn)(int(os.environ[_env])) != 0:
+        raise ValueError(f"bad {_env}")
+if os.environ.get("GAGS_B200_BLEND_IMPL"):           # 0 auto, 1 SIMT only, 2 tensor-core required
+    if lib.gags_set_blend_impl(int(os.environ["GAGS_B200_BLEND_IMPL"])) != 0:
+        raise ValueError("GAGS_B200_BLEND_IMPL must be 0, 1 or 2")
 if os.environ.get("GAGS_B200_FWD_VARIANT"):          # tuning / A-B switch, see include/gags_b200.h
     if lib.gags_set_fwd_variant(int(os.environ["GAGS_B200_FWD_VARIANT"])) != 0:
         raise ValueError("GAGS_B200_FWD_VARIANT must be 2, 3, 12 or 13")

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgags_b200.so")
 SOURCES = ["api.cu", "project.cu", "tiles.cu", "tile_buckets.cu", "sh.cu", "blend_fwd.cu", "blend_fwd_tc.cu", "blend_bwd.cu", "blend_bwd_tc.cu", "blend_bwd_cached.cu",
-           "blend_bwd_geom.cu", "train_ops.cu"]
+           "blend_bwd_geom.cu", "train_ops.cu", "pixel_losses.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -547,7 +547,6 @@ extern "C" int gags_blend_bwd_full(const float *geom, const float *colors, int32
     return gags_blend_bwd_features(geom, D, width, height, offsets, flatten_ids, v_render, v_colors,
                                    stream);
   }
-  if (D > 256) { if (want_geo) return GAGS_ERANGE; }
   if (v_colors) {
     int rc = gags_blend_bwd_features(geom, D, width, height, offsets, flatten_ids, v_render,
                                      v_colors, stream);

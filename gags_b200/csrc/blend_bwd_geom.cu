@@ -1,4 +1,4 @@
-// blend_bwd_geom.cu — K8b for wide features (32 < D <= 256): gradients of the blend w.r.t. the
+// blend_bwd_geom.cu — K8b for wide features (D > 32, in channel blocks of <= 256): gradients of the blend w.r.t. the
 // projected geometry and opacity (v_means2d, v_conics, v_opacities), SURVEY.md Appendix A.6.
 // Replaces the geometry half of gsplat rasterize_to_pixels_bwd<CDIM> (x ceil(D/32) chunk launches
 // in the reference, /root/reference/gaussian_renderer/__init__.py:56-70 -> train.py:174).
@@ -46,7 +46,7 @@ __device__ __forceinline__ int warp_reduce_scatter8(float (&v)[NV], int lane) {
 
 __global__ void __launch_bounds__(GT)
 blend_bwd_geom_wide(const float4 *__restrict__ geom, const float *__restrict__ colors, int D,
-                    const float *__restrict__ bg, int W, int H, int tile_w,
+                    int ld, const float *__restrict__ bg, int W, int H, int tile_w,
                     const int *__restrict__ offsets, const int *__restrict__ ids,
                     const float *__restrict__ render_alphas, const int *__restrict__ last_ids,
                     const float *__restrict__ v_render, const float *__restrict__ v_alphas,
@@ -93,7 +93,7 @@ blend_bwd_geom_wide(const float4 *__restrict__ geom, const float *__restrict__ c
   }
   if (!inside) for (int c = 0; c < D; ++c) vbuf[tid * VS + c] = 0.f;
   __syncthreads();
-  if (inside) bulk_g2s(vbuf + tid * VS, v_render + pix * D, rowbytes, mbar);
+  if (inside) bulk_g2s(vbuf + tid * VS, v_render + pix * ld, rowbytes, mbar);
   unsigned phase = 0;
   mbar_wait(mbar, phase); phase ^= 1u;
   const int maxlast = *s_maxlast;
@@ -117,7 +117,7 @@ blend_bwd_geom_wide(const float4 *__restrict__ geom, const float *__restrict__ c
     for (int i = tid; i < WB * 8; i += GT) s_vgeo[i] = 0.f;
     if (tid == 0) mbar_expect_tx(mbar, (unsigned)nb * rowbytes);
     __syncthreads();
-    if (tid < nb) bulk_g2s(fbuf + tid * D, colors + (size_t)s_id[tid] * D, rowbytes, mbar);
+    if (tid < nb) bulk_g2s(fbuf + tid * D, colors + (size_t)s_id[tid] * ld, rowbytes, mbar);
     // alphas for the batch (registers), while the feature rows are in flight
     float al[WB], vi[WB];
 #pragma unroll
@@ -209,20 +209,27 @@ int gags_blend_bwd_geom_wide(const float *geom, const float *colors, int32_t D,
                              const float *render_alphas, const int32_t *last_ids,
                              const float *v_render, const float *v_alphas, float *v_means2d,
                              float *v_conics, float *v_opacities, cudaStream_t st) {
-  if (D % 4 != 0 || D > 256 || D <= 32) return GAGS_ERANGE;
+  if (D % 4 != 0 || D <= 32) return GAGS_ERANGE;
   if (!gags_aligned16(colors) || !gags_aligned16(v_render)) return GAGS_EALIGN;
   const int tw = (width + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (height + HROWS - 1) / HROWS;
-  const size_t smem = (size_t)(GT * (D + 4) + WB * D) * 4 + WB * 32 + WB * 32 + WB * 4 + 8 + 16;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  // The geometry gradients are linear in the channel contractions (dot_k, Sdot, bg . v_out), so a
+  // feature width beyond what one CTA's shared memory holds is processed in channel blocks of
+  // <= 256 that all accumulate into the same outputs; the channel-free v_alpha_out term rides with
+  // the first block only.  (D <= 513 is what gsplat compiles; config 5 uses D = 512.)
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const size_t smem = (size_t)(GT * (nch + 4) + WB * nch) * 4 + WB * 32 + WB * 32 + WB * 4 + 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(blend_bwd_geom_wide,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
+    blend_bwd_geom_wide<<<dim3(tw, hh), GT, smem, st>>>(
+        reinterpret_cast<const float4 *>(geom), colors + ch0, nch, D,
+        background ? background + ch0 : nullptr, width, height, tw, offsets, flatten_ids,
+        render_alphas, last_ids, v_render + ch0, ch0 == 0 ? v_alphas : nullptr, v_means2d,
+        v_conics, v_opacities);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
   }
-  blend_bwd_geom_wide<<<dim3(tw, hh), GT, smem, st>>>(
-      reinterpret_cast<const float4 *>(geom), colors, D, background, width, height, tw, offsets,
-      flatten_ids, render_alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_opacities);
-  return (int)cudaGetLastError();
+  return 0;
 }

@@ -329,11 +329,13 @@ static int blend_fwd_impl(const float *geom, const float *colors, int32_t D, con
   if (D < 1 || width <= 0 || height <= 0) return GAGS_EINVAL;
   if (!gags_aligned16(geom)) return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc = D > 32 && D % 16 == 0 && g_gags_blend_impl != 1;
+  // D = 32 also takes the tensor-core kernel (one 64-channel atom, half of it idle): measured
+  // faster than the 16x16-tile SIMT kernel at 720p / 500 k Gaussians (BASELINE.json config 2)
+  const bool tc = D >= 32 && D % 16 == 0 && g_gags_blend_impl != 1;
   // last_ids may be NULL only where the kernel has a path that does not track it
   if (!last_ids && !gags_blend_last_ids_optional(D)) return GAGS_EINVAL;
   if (wcache && !tc) return GAGS_EINVAL;
-  if (D <= 32) {
+  if (D <= 32 && !tc) {
     if (D <= 4) return launch_narrow<4>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
     if (D <= 8) return launch_narrow<8>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
     if (D <= 16) return launch_narrow<16>(geom, colors, D, background, width, height, offsets, flatten_ids, render, alphas, last_ids, st);
@@ -371,7 +373,7 @@ extern "C" int gags_blend_fwd(const float *geom, const float *colors, int32_t D,
 
 extern int g_fwd_variant;
 extern "C" int gags_blend_last_ids_optional(int32_t D) {
-  return (D > 32 && D % 16 == 0 && g_gags_blend_impl != 1 && g_fwd_variant == 3) ? 1 : 0;
+  return (D >= 32 && D % 16 == 0 && g_gags_blend_impl != 1 && g_fwd_variant == 3) ? 1 : 0;
 }
 
 extern "C" int gags_blend_cache_supported(int32_t D) {

@@ -218,15 +218,19 @@ class PeerAdam:
                 self.timing.append(ev)
                 if len(self.timing) > 64:
                     del self.timing[:-64]
-            # re-zero the persistent gradient buffer for the next backward
+            # the parameters are final HERE: the next forward blend waits for this event only ...
+            params_done = torch.cuda.Event()
+            params_done.record(xs)
+            # ... while the re-zeroing of the persistent gradient buffer (0.3 ms of HBM writes) only
+            # has to land before the next BACKWARD and runs beside the next forward
             C.check(C.lib.gags_zero_fill(self._buf.data_ptr() + 4 * self.padded, 4 * self.padded,
                                          xs.cuda_stream), "gags_zero_fill")
             C.count_launch()
             done = torch.cuda.Event()
             done.record(xs)
         self._done = done
-        R.param_ready_events[p.data_ptr()] = done         # the next forward blend waits for this
-        R.sink_ready_events[self.grad.data_ptr()] = done  # ... and so does the next backward
+        R.param_ready_events[p.data_ptr()] = params_done  # the next forward blend waits for this
+        R.sink_ready_events[self.grad.data_ptr()] = done  # ... and the next backward for this
         p.grad = self.grad
 
     def synchronize(self) -> None:

@@ -1,8 +1,8 @@
 """GaussianModel: the per-Gaussian parameter store the renderer reads, with the reference's
 operator surface (/root/reference/scene/gaussian_model.py): getters :116-139, training_setup
-:183-212, capture/restore :63-113 (same 12-/13-tuple layout), rewrite_semantic_feature, SH degree
-stepping.  Densify/prune and PLY I/O are not exercised with frozen geometry (train.py:207) and are
-out of scope.
+:183-212, capture/restore :63-113 (same 12-/13-tuple layout), save_ply/load_ply :222-319 (plyfile-free, same
+file layout incl. semantic_{i}), rewrite_semantic_feature, SH degree stepping.  Densify/prune is not
+exercised with frozen geometry (train.py:207) and is out of scope.
 
 Two additions that do not change the surface:
   * tensors live on `device` (default "cuda") instead of a hard-coded "cuda";
@@ -57,7 +57,7 @@ class GaussianModel:
                 self.xyz_gradient_accum, self.denom, self.optimizer.state_dict(),
                 self.spatial_lr_scale, self._semantic_feature)
 
-    def restore(self, model_args, training_args):
+    def restore(self, model_args, training_args, resume_optimizer: bool = False):
         if len(model_args) == 13:       # resume a feature-field run
             (self.active_sh_degree, self._xyz, self._features_dc, self._features_rest,
              self._scaling, self._rotation, self._opacity, self.max_radii2D, xyz_gradient_accum,
@@ -72,9 +72,16 @@ class GaussianModel:
         # The reference loads the optimiser state before training_setup() rebuilds the optimiser
         # (:96 then :108), i.e. on self.optimizer from the earlier training_setup(); do the same
         # when one exists, then rebuild.
+        # NOTE this means a resumed run restarts with zero Adam moments in the reference (and here, by
+        # default).  resume_optimizer=True additionally loads the saved state into the NEW optimiser
+        # (Adam and FusedAdam share the state layout); it is an extension, off by default so that a
+        # resumed run matches the reference step for step.
         if len(model_args) == 13 and self.optimizer is not None:
             self.optimizer.load_state_dict(opt_dict)
-        self.training_setup(training_args)
+        fused = self.optimizer is not None and type(self.optimizer).__name__ == "FusedAdam"
+        self.training_setup(training_args, fused_optimizer=fused)
+        if resume_optimizer and len(model_args) == 13:
+            self.optimizer.load_state_dict(opt_dict)
         self.xyz_gradient_accum = xyz_gradient_accum
         self.denom = denom
 
@@ -113,7 +120,71 @@ class GaussianModel:
         if self.active_sh_degree < self.max_sh_degree:
             self.active_sh_degree += 1
 
-    # ---- construction from tensors (stands in for create_from_pcd / load_ply) -------------------
+    # ---- PLY I/O (scene/gaussian_model.py:222-259, :266-319), without the plyfile package ---------
+    def construct_list_of_attributes(self):
+        names = ["x", "y", "z", "nx", "ny", "nz"]
+        names += [f"f_dc_{i}" for i in range(self._features_dc.shape[1] * self._features_dc.shape[2])]
+        names += [f"f_rest_{i}" for i in
+                  range(self._features_rest.shape[1] * self._features_rest.shape[2])]
+        names.append("opacity")
+        names += [f"scale_{i}" for i in range(self._scaling.shape[1])]
+        names += [f"rot_{i}" for i in range(self._rotation.shape[1])]
+        if self._semantic_feature is not None:
+            names += [f"semantic_{i}" for i in range(self._semantic_feature.shape[1])]
+        return names
+
+    def save_ply(self, path):
+        """Same file the reference writes: one float32 `vertex` element, SH coefficients stored
+        channel-major (the [N,K,3] tensors transposed to [N,3,K] and flattened), raw (pre-activation)
+        opacity / scale / rotation, then semantic_{i}."""
+        import numpy as np
+        from ..utils.ply_io import write_vertex_ply
+        cpu = lambda t: t.detach().cpu().numpy()
+        xyz = cpu(self._xyz)
+        cols = [xyz, np.zeros_like(xyz),
+                cpu(self._features_dc.detach().transpose(1, 2).flatten(start_dim=1).contiguous()),
+                cpu(self._features_rest.detach().transpose(1, 2).flatten(start_dim=1).contiguous()),
+                cpu(self._opacity), cpu(self._scaling), cpu(self._rotation)]
+        if self._semantic_feature is not None:
+            cols.append(cpu(self._semantic_feature))
+        write_vertex_ply(path, self.construct_list_of_attributes(), np.concatenate(cols, axis=1))
+
+    def load_ply(self, path):
+        """Reads a GAGS point cloud (with semantic_{i}) or a plain 3DGS one (without; the feature
+        table then stays unset until training_setup() creates it)."""
+        import numpy as np
+        from ..utils.ply_io import read_vertex_ply
+        names, col = read_vertex_ply(path)
+        dev = self.device
+
+        def stack(prefix):
+            keys = sorted((n for n in names if n.startswith(prefix)),
+                          key=lambda x: int(x.split("_")[-1]))
+            return np.stack([col[k] for k in keys], axis=1).astype(np.float32) if keys else None
+
+        xyz = np.stack([col["x"], col["y"], col["z"]], axis=1).astype(np.float32)
+        n = xyz.shape[0]
+        f_dc = stack("f_dc_")
+        f_rest = stack("f_rest_")
+        k_rest = (self.max_sh_degree + 1) ** 2 - 1
+        if f_rest is None or f_rest.shape[1] != 3 * k_rest:
+            raise ValueError(f"{path}: expected {3 * k_rest} f_rest_* properties for SH degree "
+                             f"{self.max_sh_degree}")
+        par = lambda a: nn.Parameter(torch.tensor(a, dtype=torch.float32, device=dev)
+                                     .contiguous().requires_grad_(True))
+        self._xyz = par(xyz)
+        self._features_dc = par(f_dc.reshape(n, 3, 1).transpose(0, 2, 1))
+        self._features_rest = par(f_rest.reshape(n, 3, k_rest).transpose(0, 2, 1))
+        self._opacity = par(col["opacity"].astype(np.float32)[:, None])
+        self._scaling = par(stack("scale_"))
+        self._rotation = par(stack("rot_"))
+        sem = stack("semantic_")
+        if sem is not None:
+            self._semantic_feature = par(sem)
+        self.max_radii2D = torch.zeros(n, device=dev)
+        self.active_sh_degree = self.max_sh_degree
+
+    # ---- construction from tensors (stands in for create_from_pcd) -------------------------------
     def create_from_tensors(self, xyz, scaling, rotation, opacity, features_dc=None,
                             features_rest=None, semantic_feature=None, spatial_lr_scale=1.0):
         dev = self.device

@@ -84,8 +84,8 @@ class SynthScene:
 
 
 def make_scene(n: int, height: int, width: int, d: int, seed: int = 1234, n_views: int = 64,
-               z_range=(2.0, 20.0), sigma_px_median: float = 2.0, with_sh: bool = True
-               ) -> SynthScene:
+               z_range=(2.0, 20.0), sigma_px_median: float = 2.0, with_sh: bool = True,
+               feature_device=None) -> SynthScene:
     """Appendix B.  Means: pick a view, a uniform pixel and a depth U[z_range], un-project
     (=> uniform inside the union of the view frusta).  Scales: z*sigma_px/fx*exp(N(0,.4)) with
     sigma_px ~ LogNormal(ln 2, 0.7) => median projected sigma ~ 2 px."""
@@ -107,7 +107,13 @@ def make_scene(n: int, height: int, width: int, d: int, seed: int = 1234, n_view
     scaling = torch.log(s)
     rotation = torch.randn(n, 4, generator=g)
     opacity = 1.5 * torch.randn(n, 1, generator=g)
-    sem = 0.1 * torch.randn(n, d, generator=g)
+    if feature_device is not None:
+        # the [N, D] feature table drawn on the device (config 5: 10 GB — a minute of host RNG per
+        # rank otherwise); geometry, cameras and everything else stay on the seeded host generator
+        gd = torch.Generator(device=feature_device).manual_seed(seed + 7)
+        sem = 0.1 * torch.randn(n, d, generator=gd, device=feature_device)
+    else:
+        sem = 0.1 * torch.randn(n, d, generator=g)
     if with_sh:
         f_dc = torch.rand(n, 1, 3, generator=g) * 2.0 - 1.0
         f_rest = 0.05 * torch.randn(n, 15, 3, generator=g)
@@ -124,6 +130,11 @@ def make_target(height: int, width: int, d: int, seed: int) -> torch.Tensor:
     return 0.1 * torch.randn(height, width, d, generator=g)
 
 
-def config_scene(config_id: int, n_views: int = 64, with_sh: bool = False) -> SynthScene:
+def config_scene(config_id: int, n_views: int = 64, with_sh: bool = False,
+                 feature_device=None) -> SynthScene:
+    """`feature_device`: draw the feature table there when it is huge (> 1.5e9 values, i.e. config 5);
+    smaller tables always come from the host generator so that every run sees the same scene."""
     n, h, w, d = CONFIGS[config_id]
-    return make_scene(n, h, w, d, seed=1234 + config_id, n_views=n_views, with_sh=with_sh)
+    dev = feature_device if n * d > 1_500_000_000 else None
+    return make_scene(n, h, w, d, seed=1234 + config_id, n_views=n_views, with_sh=with_sh,
+                      feature_device=dev)

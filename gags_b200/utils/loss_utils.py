@@ -12,7 +12,49 @@ def l1_loss(network_output, gt):
     return torch.abs(network_output - gt).mean()
 
 
+def _rows_ok(network_output, gt) -> bool:
+    """CUDA [D,H,W] float32 pair with D % 4 == 0 whose first argument needs no gradient to `gt`."""
+    return (network_output.is_cuda and gt.is_cuda and network_output.dim() == 3
+            and network_output.shape == gt.shape and network_output.dtype == torch.float32
+            and gt.dtype == torch.float32 and network_output.shape[0] % 4 == 0
+            and not gt.requires_grad)
+
+
+class _PixelLoss(torch.autograd.Function):
+    """mode 0: l1_loss_map, mode 1: per-pixel cosine similarity (csrc/pixel_losses.cu)."""
+
+    @staticmethod
+    def forward(ctx, mode, a_hwd, b_hwd):
+        a, b = a_hwd.contiguous(), b_hwd.contiguous()
+        H, W, D = a.shape
+        out = torch.empty(H, W, dtype=torch.float32, device=a.device)
+        stats = torch.empty(H, W, 2, dtype=torch.float32, device=a.device) if mode == 1 else None
+        _C.check(_C.lib.gags_pixel_loss_fwd(mode, _C.ptr(a), _C.ptr(b), H * W, D, _C.ptr(out),
+                                            _C.ptr(stats), _C.stream_ptr()), "gags_pixel_loss_fwd")
+        _C.count_launch()
+        ctx.mode = mode
+        ctx.save_for_backward(a, b, out, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, out, stats = ctx.saved_tensors
+        H, W, D = a.shape
+        va = torch.empty_like(a)
+        _C.check(_C.lib.gags_pixel_loss_bwd(ctx.mode, _C.ptr(a), _C.ptr(b),
+                                            _C.ptr(g.contiguous().to(torch.float32)), _C.ptr(out),
+                                            _C.ptr(stats), H * W, D, _C.ptr(va), _C.stream_ptr()),
+                 "gags_pixel_loss_bwd")
+        _C.count_launch()
+        return None, va, None
+
+
 def l1_loss_map(network_output, gt):
+    """mean(|a - b|, dim=0) -> [H,W] (utils/loss_utils.py:23-24).  On CUDA [D,H,W] maps this is one
+    row-reduction kernel over the channel-last rows (a permuted view of the raster is free; a
+    [D,H,W]-contiguous target is transposed once); anything else takes the eager form."""
+    if _rows_ok(network_output, gt):
+        return _PixelLoss.apply(0, network_output.permute(1, 2, 0), gt.permute(1, 2, 0))
     return torch.abs(network_output - gt).mean(dim=0)
 
 
@@ -21,6 +63,9 @@ def l2_loss(network_output, gt):
 
 
 def cos_loss(network_output, gt):
+    """1 - mean over pixels of the channel cosine similarity (utils/loss_utils.py:29-30)."""
+    if _rows_ok(network_output, gt):
+        return 1 - _PixelLoss.apply(1, network_output.permute(1, 2, 0), gt.permute(1, 2, 0)).mean()
     return 1 - F.cosine_similarity(network_output, gt, dim=0).mean()
 
 

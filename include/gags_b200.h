@@ -216,7 +216,8 @@ int gags_blend_bwd_features_cached_l1(int32_t D, int32_t width, int32_t height,
                                       float *loss_out, float *v_colors, void *stream);
 
 /* K8b full backward (replaces rasterize_to_pixels_bwd; App. A.6).  Outputs must be
- * zero-initialised; v_colors may be NULL (skip), v_alphas may be NULL (= 0).  D <= 256.
+ * zero-initialised; v_colors may be NULL (skip), v_alphas may be NULL (= 0).  Any D gsplat accepts
+ * (wide D runs in channel blocks of 256 that accumulate into the same geometry gradients).
  * Out: v_means2d[N,2] v_conics[N,3] v_opacities[N] v_colors[N,D]                              */
 int gags_blend_bwd_full(const float *geom, const float *colors, int32_t D,
                         const float *background, int32_t width, int32_t height,
@@ -261,6 +262,16 @@ int gags_blend_bwd_features_cached_sam(int32_t D, int32_t width, int32_t height,
                                        const float *scale_map3, int32_t n_seg, float grad_scale,
                                        float *loss_out, float *v_scale_map, float *v_colors,
                                        void *stream);
+
+/* Per-pixel losses over the channel dimension of channel-last rows a, b [HW, D] (D % 4 == 0):
+ *   mode 0 = l1_loss_map (/root/reference/utils/loss_utils.py:23-24): out[p] = mean_c |a - b|;
+ *   mode 1 = the per-pixel cosine similarity of cos_loss (:29-30, eps 1e-8); stats[HW][2] = |a|, |b|.
+ * gags_pixel_loss_bwd gives v_a = g[p] * d out[p] / d a (b is the target).                         */
+int gags_pixel_loss_fwd(int32_t mode, const float *a, const float *b, int64_t HW, int32_t D,
+                        float *out, float *stats, void *stream);
+int gags_pixel_loss_bwd(int32_t mode, const float *a, const float *b, const float *g,
+                        const float *out, const float *stats, int64_t HW, int32_t D, float *v_a,
+                        void *stream);
 
 /* v[0..numel) *= *scale_dev (a DEVICE scalar), a no-op pass when the scalar is exactly 1: chains the
  * fused loss's stored gradient with autograd's incoming grad_output without a host sync and, in the

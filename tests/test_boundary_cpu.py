@@ -158,3 +158,125 @@ def test_read_sam_clip_feature_dense_route_matches_restatement():
             assert torch.equal(ma, mb) and float((a - b).abs().max()) < 1e-6
     fm, m = mine(emb, seg, torch.softmax(torch.randn(3, H, W, generator=g), 0), median_mode=True)
     assert fm.shape == (D, H, W) and m.shape == (1, H, W)
+
+
+def test_ply_round_trip_and_layout(tmp_path):
+    """save_ply / load_ply (/root/reference/scene/gaussian_model.py:222-319) without plyfile: header
+    and property order as the reference writes them, SH stored channel-major, semantic_{i} kept; a
+    plain 3DGS file (no semantic_*) and an ascii file load too."""
+    import numpy as np
+    import torch
+    from gags_b200.scene import GaussianModel
+    from gags_b200.utils.ply_io import read_vertex_ply, write_vertex_ply
+    g = torch.Generator().manual_seed(0)
+    n, D = 37, 16
+    pc = GaussianModel(3, device="cpu")
+    pc.create_from_tensors(torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g),
+                           torch.randn(n, 4, generator=g), torch.randn(n, 1, generator=g),
+                           torch.randn(n, 1, 3, generator=g), torch.randn(n, 15, 3, generator=g),
+                           torch.randn(n, D, generator=g))
+    path = str(tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply")
+    pc.save_ply(path)
+    raw = open(path, "rb").read()
+    head = raw[:raw.index(b"end_header\n") + 11].decode().splitlines()
+    assert head[:3] == ["ply", "format binary_little_endian 1.0", f"element vertex {n}"]
+    props = [l.split()[-1] for l in head if l.startswith("property")]
+    assert props == pc.construct_list_of_attributes()
+    assert props[:6] == ["x", "y", "z", "nx", "ny", "nz"] and props[6] == "f_dc_0"
+    assert props[9] == "f_rest_0" and props[54] == "opacity" and props[-1] == f"semantic_{D - 1}"
+    assert all(l.split()[1] == "float" for l in head if l.startswith("property"))
+    assert len(raw) == raw.index(b"end_header\n") + 11 + n * len(props) * 4
+    # channel-major SH: f_rest_k = features_rest[:, k % 15, k // 15]
+    _, col = read_vertex_ply(path)
+    assert np.allclose(col["f_rest_16"], pc._features_rest[:, 1, 1].detach().numpy())
+    assert np.allclose(col["nx"], 0.0)
+    q = GaussianModel(3, device="cpu")
+    q.load_ply(path)
+    for a in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation",
+              "_semantic_feature"):
+        assert torch.equal(getattr(q, a).detach(), getattr(pc, a).detach()), a
+        assert getattr(q, a).requires_grad
+    assert q.active_sh_degree == 3 and q.max_radii2D.shape == (n,)
+    # a vanilla 3DGS cloud: no semantic_* properties
+    names = [p_ for p_ in props if not p_.startswith("semantic_")]
+    cols = np.stack([col[k] for k in names], axis=1)
+    plain = str(tmp_path / "plain.ply")
+    write_vertex_ply(plain, names, cols)
+    r = GaussianModel(3, device="cpu")
+    r.load_ply(plain)
+    assert r._semantic_feature is None and torch.equal(r._xyz.detach(), pc._xyz.detach())
+    # ascii flavour
+    asc = str(tmp_path / "ascii.ply")
+    with open(asc, "w") as f:
+        f.write("ply\nformat ascii 1.0\ncomment test\nelement vertex 2\n")
+        f.write("".join(f"property float {k}\n" for k in names) + "end_header\n")
+        for i in range(2):
+            f.write(" ".join(repr(float(v)) for v in cols[i]) + "\n")
+    a = GaussianModel(3, device="cpu")
+    a.load_ply(asc)
+    assert torch.allclose(a._xyz.detach(), pc._xyz.detach()[:2])
+
+
+def test_feature_files_round_trip(tmp_path):
+    import numpy as np
+    from gags_b200.utils.ply_io import load_feature_files, save_feature_files
+    emb = np.random.default_rng(0).standard_normal((5, 512)).astype(np.float32)
+    seg = np.random.default_rng(1).integers(-1, 5, (4, 12, 9)).astype(np.float32)
+    pre = str(tmp_path / "frame_00001")
+    save_feature_files(pre, emb, seg)
+    e2, s2 = load_feature_files(pre)
+    assert np.array_equal(e2, emb) and np.array_equal(s2, seg)
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        load_feature_files(str(tmp_path / "missing"))
+
+
+def _reference_decoder_forward(kind, mod, x):
+    """The reference's forward (/root/reference/models/networks.py:163-218 and :236-248) through the
+    module's own nn.Conv2d layers on the NCHW-style [C,H,W] map."""
+    import torch.nn.functional as F
+    d = mod.decoder
+    if kind == "scale":
+        for m in d:
+            x = m(x)
+        return F.softmax(x, dim=0)
+    x1 = d[1](d[0](x))
+    x2 = d[5](d[4](d[3](d[2](x1))))
+    x3 = d[7](d[6](x1 + x2))
+    x4 = d[11](d[10](d[9](d[8](x3))))
+    x5 = d[16](d[15](d[14](d[13](d[12](x3 + x4)))))
+    return F.normalize(x5, dim=0)
+
+
+def test_decoders_match_conv_stack_and_keep_state_dict_layout():
+    import torch
+    from gags_b200.models import CNN_decoder, CNN_scale_decoder
+    torch.manual_seed(0)
+    H, W = 13, 17
+    raster = torch.randn(H, W, 16)                       # channel-last, as the rasteriser writes it
+    x = raster.permute(2, 0, 1)                          # what render()["render"] is
+    dec = CNN_decoder(16, 512, device="cpu")
+    sca = CNN_scale_decoder(16, 3, device="cpu")
+    assert [k for k in dec.state_dict()][:2] == ["decoder.0.weight", "decoder.0.bias"]
+    assert dec.state_dict()["decoder.0.weight"].shape == (256, 16, 1, 1)
+    assert dec.state_dict()["decoder.16.weight"].shape == (512, 256, 1, 1)
+    assert sca.state_dict()["decoder.10.weight"].shape == (3, 16, 1, 1)
+    for kind, mod, cout in (("feature", dec, 512), ("scale", sca, 3)):
+        xa = x.clone().requires_grad_(True)
+        xb = x.clone().requires_grad_(True)
+        ya = mod(xa)
+        yb = _reference_decoder_forward(kind, mod, xb.unsqueeze(0)[0])
+        assert ya.shape == (cout, H, W)
+        assert float((ya - yb).abs().max()) < 1e-5
+        g = torch.randn_like(ya)
+        mod.zero_grad()
+        (ya * g).sum().backward()
+        ga = [p.grad.clone() for p in mod.parameters()]
+        mod.zero_grad()
+        (yb * g).sum().backward()
+        gb = [p.grad.clone() for p in mod.parameters()]
+        assert float((xa.grad - xb.grad).abs().max()) < 1e-4
+        for a, b in zip(ga, gb):
+            assert float((a - b).abs().max()) < 1e-3 * max(1.0, float(b.abs().max()))
+    # the result is again a [C,H,W] view of a channel-last buffer (feeds the fused losses directly)
+    assert dec(x).permute(1, 2, 0).is_contiguous()

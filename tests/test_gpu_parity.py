@@ -288,7 +288,7 @@ def test_tensor_core_feature_backward_matches_simt_and_oracle(D, n, opac_lo, ble
     assert rel_err(grads[3], grads[2]) < 1e-5
 
 
-@pytest.mark.parametrize("D", [3, 4, 16, 32, 64, 256])
+@pytest.mark.parametrize("D", [3, 4, 16, 32, 64, 256, 512])
 def test_full_backward_matches_oracle(D):
     from gags_b200 import rasterization as R
     W, H = 64, 48

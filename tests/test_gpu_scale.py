@@ -503,3 +503,121 @@ def test_fused_sam_backward_equals_loss_then_backward(D, want_vs):
         assert rel_err(v1, v0) < 1e-5
     else:
         assert v1 is None
+
+
+@pytest.mark.parametrize("D", [16, 64, 256])
+def test_l1_loss_map_and_cos_loss_kernels_match_eager(D):
+    """utils/loss_utils.py:23-30 on the device path: row-reduction kernels vs the eager statements,
+    values and gradients w.r.t. the render (channel-last view and [D,H,W]-contiguous inputs)."""
+    import torch.nn.functional as F
+    from gags_b200.utils.loss_utils import cos_loss, l1_loss_map
+    g = torch.Generator().manual_seed(D)
+    H, W = 37, 53
+    raster = torch.randn(H, W, D, generator=g).cuda()
+    gt = torch.randn(D, H, W, generator=g).cuda()
+    raster[3, 5] = 0.0                                            # a zero-norm pixel (cosine eps path)
+    wmap = torch.rand(H, W, generator=g).cuda()
+    for view in (True, False):
+        src = raster.permute(2, 0, 1) if view else raster.permute(2, 0, 1).contiguous()
+        a = src.clone().requires_grad_(True) if not view else \
+            raster.clone().requires_grad_(True)
+        xa = a.permute(2, 0, 1) if view else a
+        b = src.detach().clone().double().requires_grad_(True)
+        la = l1_loss_map(xa, gt)
+        (la * wmap).sum().backward()
+        lb = torch.abs(b - gt.double()).mean(dim=0)
+        (lb * wmap.double()).sum().backward()
+        ga = a.grad.permute(2, 0, 1) if view else a.grad
+        assert la.shape == (H, W) and rel_err(la, lb) < 1e-6
+        assert rel_err(ga, b.grad) < 1e-6
+        a.grad = None
+        b.grad = None
+        ca = cos_loss(xa, gt)
+        ca.backward()
+        cb = 1 - F.cosine_similarity(b, gt.double(), dim=0).mean()
+        cb.backward()
+        ga = a.grad.permute(2, 0, 1) if view else a.grad
+        assert abs(float(ca) - float(cb)) < 1e-6
+        assert rel_err(ga, b.grad) < 1e-5
+
+
+# ---- known-answer tests of SURVEY Appendix C on the GPU kernels --------------------------------------
+def _kat_render(means, scales, opac, colors, W=32, H=32, bg=None, quats=None, fx=None):
+    """Activated Gaussians in front of an identity camera through rasterize_view()."""
+    from gags_b200 import rasterization as R
+    import math
+    dev = torch.device("cuda:0")
+    n = means.shape[0]
+    fx = fx or W / (2 * math.tan(math.radians(60) / 2))
+    q = quats if quats is not None else torch.tensor([[1.0, 0, 0, 0]]).repeat(n, 1)
+    old = R.want_last_ids
+    R.want_last_ids = True
+    try:
+        out = R.rasterize_view(means.to(dev), q.to(dev), scales.to(dev), opac.to(dev),
+                               colors.to(dev), torch.eye(4, device=dev), fx, fx, W / 2.0, H / 2.0,
+                               W, H, background=None if bg is None else bg.to(dev))
+    finally:
+        R.want_last_ids = old
+    return out, fx
+
+
+@pytest.mark.parametrize("D", [3, 64])
+def test_kat_alpha_threshold_and_opaque_stack(D):
+    """App. C-3: alpha just below / above 1/255 is skipped / kept; a stack of opaque Gaussians stops
+    when T' <= 1e-4, the stopping Gaussian contributes nothing, last_ids = last contributor."""
+    W = H = 32
+    z = 5.0
+    # one isotropic Gaussian centred on pixel (16,16)'s centre; at the centre alpha = opacity
+    ctr = torch.tensor([[0.5 * z / 27.7128, 0.5 * z / 27.7128, z]])      # (16.5 - 16) * z / fx
+    sc = torch.full((1, 3), 0.5)
+    for op, kept in ((1.0 / 255.0 - 2e-5, False), (1.0 / 255.0 + 2e-5, True)):
+        (r, a, info), fx = _kat_render(ctr, sc, torch.tensor([op]), torch.ones(1, D), W, H)
+        centre = float(a[16, 16])
+        assert (centre > 0) == kept
+        if kept:
+            assert abs(centre - op) < 1e-6 and abs(float(r[16, 16, 0]) - op) < 1e-6
+    # 6 opaque Gaussians (alpha clamps to 0.999) at increasing depth: T after k = 1e-3^k
+    n = 6
+    means = ctr.repeat(n, 1)
+    means[:, 2] = z + torch.arange(n) * 0.5
+    means[:, :2] = means[:, :2] * (means[:, 2:3] / z)                  # same pixel at every depth
+    cols = torch.arange(1, n + 1, dtype=torch.float32)[:, None].repeat(1, D)
+    (r, a, info), _ = _kat_render(means, sc.repeat(n, 1), torch.ones(n), cols, W, H)
+    # k=0: w = 0.999, T = 1e-3; k=1: T' = 1e-6 <= 1e-4 -> STOP, contributes nothing
+    assert abs(float(a[16, 16]) - 0.999) < 1e-6
+    assert abs(float(r[16, 16, 0]) - 0.999 * 1.0) < 1e-5
+    assert int(info["last_ids"][16, 16]) == int(info["isect_offsets"].reshape(-1)[W // 16 + 1])
+
+
+def test_kat_culls_and_background_replication():
+    """App. C-4: behind the near plane, far outside the image, degenerate covariance -> radii 0, no
+    intersections, zero gradient rows.  App. C-9: feature mode replicates bg[0] into every channel
+    (gaussian_renderer/__init__.py:47)."""
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.synthetic import make_scene
+    W = H = 32
+    means = torch.tensor([[0.0, 0.0, 5.0],       # visible
+                          [0.0, 0.0, -1.0],      # behind the camera
+                          [0.0, 0.0, 0.005],     # in front of z = 0 but inside the near plane (0.01)
+                          [400.0, 0.0, 5.0],     # far outside the frustum
+                          [0.0, 0.0, 5.0]])      # NaN scale -> det test fails
+    sc = torch.full((5, 3), 0.3)
+    sc[4] = float("nan")
+    cols = torch.nn.Parameter(torch.ones(5, 64).cuda())
+    (r, a, info), _ = _kat_render(means, sc, torch.full((5,), 0.8), cols, W, H)
+    assert info["radii"].tolist()[0] > 0 and info["radii"].tolist()[1:] == [0, 0, 0, 0]
+    assert int(info["tiles_per_gauss"][1:].sum()) == 0
+    assert set(info["flatten_ids"].tolist()) == {0}
+    r.sum().backward()
+    assert float(cols.grad[0].abs().sum()) > 0 and float(cols.grad[1:].abs().sum()) == 0.0
+    # background replication through render()
+    dev = torch.device("cuda:0")
+    scene = make_scene(50, 48, 64, 16, seed=2, n_views=2)
+    pc = _model(scene, dev)
+    bgc = torch.tensor([0.7, 0.1, 0.2], device=dev)
+    with torch.no_grad():
+        img = render(scene.cameras[0].to(dev), pc, None, bgc)["render"]
+        blk = render(scene.cameras[0].to(dev), pc, None, torch.zeros(3, device=dev))["render"]
+    diff = img - blk                                   # = T_final * bg, identical in every channel
+    assert float(diff.max()) > 0.5
+    assert float((diff - diff[0:1]).abs().max()) < 1e-6
