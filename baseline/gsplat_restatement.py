@@ -46,10 +46,16 @@ class _ChunkBlend(torch.autograd.Function):
         render = torch.empty(height, width, D, dtype=torch.float32, device=dev)
         alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
         last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
-        _C.check(_C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height,
+        # pin the SIMT kernels: the product would route a 32-channel chunk to its tensor-core kernel
+        prev = _C.lib.gags_get_blend_impl()
+        _C.check(_C.lib.gags_set_blend_impl(1))
+        try:
+            rc = _C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height,
                                        _C.ptr(offsets), _C.ptr(flatten_ids), _C.ptr(render),
-                                       _C.ptr(alphas), _C.ptr(last_ids), _C.stream_ptr()),
-                 "gags_blend_fwd")
+                                       _C.ptr(alphas), _C.ptr(last_ids), _C.stream_ptr())
+        finally:
+            _C.lib.gags_set_blend_impl(prev)
+        _C.check(rc, "gags_blend_fwd")
         _C.count_launch()
         ctx.dims = (width, height, D, N)
         ctx.save_for_backward(colors, geom, offsets, flatten_ids, bg, alphas, last_ids)

@@ -500,8 +500,11 @@ extern "C" int gags_adam_step_peer(int32_t world, int32_t rank, const uint64_t *
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  const long long cap_u = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 4);
-  if (blocks > cap_u) blocks = cap_u;                          // default: half the thread slots free
+  // Default 2 CTAs/SM: the exchange runs beside the NEXT view's projection / tile sort on the main
+  // stream; with 4 CTAs/SM the projection kernel was starved (2.9 ms instead of 0.1 ms in the 2-GPU
+  // trace, profiles/r02b_trace_dp2.txt) and the forward behind it started 0.6 ms late.
+  const long long cap_u = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
+  if (blocks > cap_u) blocks = cap_u;
 #define GAGS_PEER_LAUNCH(MAXW)                                                                   \
   adam_peer_kernel<MAXW><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                      \
       pp, world, rank, reinterpret_cast<float4 *>(exp_avg_shard),                                  \
@@ -535,8 +538,11 @@ extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long long c4 = count / 4;
   long long blocks = (c4 + 255) / 256;
-  const long long cap_m = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
-  if (blocks > cap_m) blocks = cap_m;                          // small grid, 4 reductions per thread
+  // Default 1 CTA/SM: the 8-GPU sweep (profiles/r02a_peer_rate_8gpu.txt) shows the NVLS form at the
+  // same 4.2-4.4 ms from 1 to 8 CTAs/SM (it is bound by the switch, not by requests in flight), and
+  // the smallest grid leaves the SMs to the next view's projection / sort running beside it.
+  const long long cap_m = gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 1);
+  if (blocks > cap_m) blocks = cap_m;
 #define GAGS_MC_LAUNCH(U)                                                                        \
   adam_multicast_kernel<U><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                   \
       reinterpret_cast<const float4 *>(mc_grad), reinterpret_cast<float4 *>(mc_param),             \
