@@ -416,6 +416,16 @@ def main():
             extras["dense_target"] = dense_target_leg(locals())
             torch.cuda.empty_cache()
 
+    # ---- N > 1: who waits for whom (every rank's average wait at the opening barrier) ------------
+    wait_by_rank = None
+    if peer is not None and peer.timing_summary() is not None:
+        ts = peer.timing_summary()
+        mine = torch.tensor([ts["barrier_in_ms"], ts["kernel_ms"]], dtype=torch.float64, device=dev)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        wait_by_rank = {"wait_slowest_rank_ms": [round(float(v[0]), 3) for v in allv],
+                        "exchange_kernel_ms": [round(float(v[1]), 3) for v in allv]}
+
     # ---- per-stage device times for the roofline (rank 0, single views, CUDA events) -------------
     stage_ms, stats, roofline = {}, {}, None
     if rank == 0:
@@ -440,6 +450,10 @@ def main():
                     pkg = render_view(cam)
             else:
                 pkg = render_view(cam)
+                hnd = getattr(pkg["render"], "_gags_fused", None)
+                if i == 0 and hnd is not None and hnd.ctx.lease is not None:
+                    n_half = ((W + 15) // 16) * ((H + 7) // 8)
+                    stats["cached_weight_tiles"] = int(hnd.ctx.lease.bufs[3][:n_half].sum())
                 R._mark("loss_start")
                 if args.unfused_loss:
                     loss = l1_loss_segmap_fused(pkg["render"], targets_dev[0][0], targets_dev[0][1])
@@ -485,9 +499,12 @@ def main():
             if cfg in (3, 4):
                 tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                 traffic = tj[kname]
-                non_alg = tj.get(kname + "_non_algorithmic")
         except Exception:
             pass
+        # the weight-tile cache (16 KB tile + 32 ids + list entry per blended batch): written by the
+        # training forward, re-read by the backward — DRAM traffic that is not algorithmic
+        if "cached_weight_tiles" in stats:
+            non_alg = stats["cached_weight_tiles"] * (16384 + 128 + 4)
         roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "peak_kind": peak_kind,
                     "traffic": traffic, "non_algorithmic_bytes": non_alg,
@@ -505,6 +522,7 @@ def main():
         if peer is not None and peer.timing_summary() is not None:
             ps = peer.timing_summary()
             stats["peer_step_ms"] = ps
+            stats["peer_by_rank"] = wait_by_rank
             stage_ms.pop("adam", None)
             stage_ms["exchange_wait_slowest_rank"] = ps["barrier_in_ms"]
             stage_ms["exchange_kernel"] = ps["kernel_ms"]

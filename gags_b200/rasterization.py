@@ -121,7 +121,11 @@ def _readback_state(dev):
     return st
 
 
-_pending_prezero = None
+# Hand-offs between rasterize_view() and the autograd nodes it creates (the pre-zeroed gradient
+# buffer, the context of the forward that kept its weight tiles).  They live for the duration of ONE
+# rasterize_view() call on ONE thread: thread-local, and cleared when the call ends however it ends.
+import threading as _threading
+_tls = _threading.local()
 
 
 def _early_prezero(colors, geo_in, sh_degree) -> None:
@@ -130,8 +134,7 @@ def _early_prezero(colors, geo_in, sh_degree) -> None:
     bound and leave HBM idle, whereas the forward and backward blends fill the register file and
     the optimiser pass is HBM bound — nothing can run in THEIR shadow (measured: a fill launched
     right behind the forward starts when the forward drains)."""
-    global _pending_prezero
-    _pending_prezero = None
+    _tls.pending_prezero = None
     if not (prezero_overlap and stage_events is None and weight_cache and sh_degree is None
             and torch.is_grad_enabled() and colors.is_cuda and colors.requires_grad
             and colors.dim() == 2 and not any(t.requires_grad for t in geo_in)):
@@ -155,7 +158,7 @@ def _early_prezero(colors, geo_in, sh_degree) -> None:
         _C.count_launch()
         evz = torch.cuda.Event()
         evz.record(zs)
-    _pending_prezero = (vz, evz, torch.cuda.current_stream(dev))
+    _tls.pending_prezero = (vz, evz, torch.cuda.current_stream(dev))
 
 
 def _zero_stream(dev):
@@ -341,7 +344,8 @@ def tile_bits(n_tiles: int) -> int:
     return int(math.floor(math.log2(n_tiles))) + 1
 
 
-_isect_capacity = 0
+# grow-only capacity of the intersection buffers, per device (index -> entries)
+_isect_capacity: Dict[int, int] = {}
 # True = K4-K6 through the tile-bucketed segmented sort (csrc/tile_buckets.cu); False = count /
 # scan / emit / global cub radix sort / offsets (csrc/tiles.cu).  Both give identical arrays
 # (tests/test_gpu_parity.py::test_tile_stage_is_bit_exact).  Measured at config 3 on B200: 0.57 ms
@@ -361,7 +365,8 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
     N = radii.shape[0]
     dev = radii.device
     st = _C.stream_ptr()
-    global _isect_capacity
+    cap_key = dev.index if dev.index is not None else torch.cuda.current_device()
+    known_cap = _isect_capacity.get(cap_key, 0)
     if bucket_sort:
         # tile-bucketed segmented sort: scatter + scan give the offsets and n_isects directly
         n_tiles = tile_w * tile_h
@@ -379,7 +384,7 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
         # back, so the device sorts during the host round trip; its guard skips tiles that do not
         # fit, and the (rare) view that outgrew the capacity is sorted again below.
         keys = vals = None
-        spec_cap = _isect_capacity if (speculative_sort and after_count is None) else 0
+        spec_cap = known_cap if (speculative_sort and after_count is None) else 0
         if spec_cap > 0:
             main = torch.cuda.current_stream(dev)
             ev_counts = torch.cuda.Event()
@@ -408,9 +413,9 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
             if spec_cap > 0 and n <= spec_cap:
                 return dict(n_isects=n, isect_ids=keys[:n], flatten_ids=vals[:n], offsets=offsets,
                             cum_tiles=None, _bases=(keys, vals, offsets))
-            if n > _isect_capacity:
-                _isect_capacity = int(n * 1.2) + 1024
-            cap = _isect_capacity
+            if n > known_cap:
+                known_cap = _isect_capacity[cap_key] = int(n * 1.2) + 1024
+            cap = known_cap
             keys = torch.empty(cap, dtype=torch.int64, device=dev)
             vals = torch.empty(cap, dtype=torch.int32, device=dev)
             if n > 0:
@@ -435,9 +440,9 @@ def bin_and_sort(means2d, radii, depths, tiles_touched, tile_w: int, tile_h: int
     # n varies by a few percent from view to view; allocating a grow-only capacity instead keeps
     # every view's request the same size, so the caching allocator recycles blocks instead of
     # calling cudaMalloc (a device-wide sync) every other view
-    if n > _isect_capacity:
-        _isect_capacity = int(n * 1.2) + 1024
-    cap = _isect_capacity
+    if n > known_cap:
+        known_cap = _isect_capacity[cap_key] = int(n * 1.2) + 1024
+    cap = known_cap
     keys_a = torch.empty(cap, dtype=torch.int64, device=dev)
     keys_b = torch.empty(cap, dtype=torch.int64, device=dev)
     vals_a = torch.empty(cap, dtype=torch.int32, device=dev)
@@ -503,9 +508,6 @@ class _FusedHandle:
 
     def __init__(self, ctx, cols, offsets, render_ptr):
         self.ctx, self.cols, self.offsets, self.render_ptr = ctx, cols, offsets, render_ptr
-
-
-_last_cached_ctx = None
 
 
 def _fused_handle(render_dhw):
@@ -673,14 +675,12 @@ class _Blend(torch.autograd.Function):
         # pure HBM stream, the forward above is instruction-bound with its shared memory full: the
         # fill runs beside it on the side stream instead of in front of the backward.
         ctx.prezero = None
-        global _pending_prezero
-        if cache is not None and _pending_prezero is not None \
-                and _pending_prezero[0].shape == (N, D):
-            ctx.prezero = _pending_prezero
-        _pending_prezero = None
+        pending = getattr(_tls, "pending_prezero", None)
+        if cache is not None and pending is not None and pending[0].shape == (N, D):
+            ctx.prezero = pending
+        _tls.pending_prezero = None
         ctx.lease = lease if cache is not None else None
-        global _last_cached_ctx
-        _last_cached_ctx = ctx if cache is not None else None
+        _tls.last_cached_ctx = ctx if cache is not None else None
         ctx.save_for_backward(colors, bg, geom, offsets, flatten_ids, alphas, last_ids)
         if last_ids is not None:
             ctx.mark_non_differentiable(last_ids)
@@ -821,12 +821,11 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
                                             binned["offsets"], binned["flatten_ids"], width, height)
     _mark("blend_fwd")
-    global _last_cached_ctx
-    if _last_cached_ctx is not None:
+    last_ctx = getattr(_tls, "last_cached_ctx", None)
+    if last_ctx is not None:
         if not pad and render_mode == "RGB":
-            render._gags_fused = _FusedHandle(_last_cached_ctx, cols, binned["offsets"],
-                                              render.data_ptr())
-        _last_cached_ctx = None
+            render._gags_fused = _FusedHandle(last_ctx, cols, binned["offsets"], render.data_ptr())
+        _tls.last_cached_ctx = None
     if use_side:
         ss["ev_prev"] = torch.cuda.Event()
         ss["ev_prev"].record(main)

@@ -280,3 +280,18 @@ def test_decoders_match_conv_stack_and_keep_state_dict_layout():
             assert float((a - b).abs().max()) < 1e-3 * max(1.0, float(b.abs().max()))
     # the result is again a [C,H,W] view of a channel-last buffer (feeds the fused losses directly)
     assert dec(x).permute(1, 2, 0).is_contiguous()
+
+
+def test_product_eval_sh_matches_reference_golden(golden):
+    """gags_b200.utils.sh_utils.eval_sh (same signature as /root/reference/utils/sh_utils.py:57-112)
+    against the outputs of the reference's own eval_sh (tests/golden/reference_utils.npz)."""
+    import torch
+    from gags_b200.utils.sh_utils import RGB2SH, SH2RGB, eval_sh
+    dirs = torch.from_numpy(golden["sh_dirs"])
+    sh = torch.from_numpy(golden["sh_coeffs"])            # [n, 3, 25]
+    for deg in range(4):
+        got = eval_sh(deg, sh, dirs)
+        ref = torch.from_numpy(golden[f"sh_out_deg{deg}"])
+        assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12), deg
+    x = torch.rand(5, 3)
+    assert torch.allclose(SH2RGB(RGB2SH(x)), x, atol=1e-6)

@@ -116,13 +116,14 @@ def test_speculative_bucket_sort_matches_oracle(cap0):
     the oracle's arrays; a second call then runs on the capacity the first one left."""
     from gags_b200 import rasterization as R
     sc = front_scene(6000, 200, 120, 3, seed=21, sigma_px=(0.5, 12.0))
-    old = R._isect_capacity
+    key = torch.cuda.current_device()
+    old = R._isect_capacity.get(key, 0)
     try:
-        R._isect_capacity = cap0
+        R._isect_capacity[key] = cap0
         runs = [_stages(sc), _stages(sc)]
-        assert R._isect_capacity >= runs[0]["n_isects"]
+        assert R._isect_capacity[key] >= runs[0]["n_isects"]
     finally:
-        R._isect_capacity = max(old, R._isect_capacity)
+        R._isect_capacity[key] = max(old, R._isect_capacity[key])
     m2d, radii, dep = runs[0]["means2d"].cpu(), runs[0]["radii"].cpu(), runs[0]["depths"].cpu()
     _, keys, vals = O.isect_tiles(m2d, radii, dep, runs[0]["tw"], runs[0]["th"])
     for st in runs:
@@ -307,8 +308,10 @@ def test_full_backward_matches_oracle(D):
     out, alphas, _ = R._Blend.apply(gl[0], gl[1], gl[2], gl[3], bg.cuda(), st["geom"], st["offsets"],
                                     st["flatten_ids"], W, H)
     ((out * v_out.cuda()).sum() + (alphas * v_alpha.cuda()).sum()).backward()
+    # 1e-4 of scale against the fp64 oracle on identical inputs; the budget covers pixels where the
+    # fp32 kernel and the oracle disagree on an alpha / transmittance threshold (helpers docstring)
     for name, a, b in zip(("means2d", "conics", "opac", "colors"), gl, leaves):
-        assert frac_bad(a.grad, b.grad, 2e-4) < 1e-3, name
+        assert frac_bad(a.grad, b.grad, RTOL) < 2e-3, name
         assert rel_err(a.grad, b.grad) < 2e-2, name
 
 
@@ -367,9 +370,11 @@ def test_projection_backward_matches_oracle_autograd():
      + (o2 * v_o.cuda()).sum()).backward()
     same = (r2.cpu() > 0) == (radii > 0)
     assert float(same.double().mean()) > 0.998
+    # 1e-4 of scale; the budget covers Gaussians on the frustum-clamp / det / radius decision edges,
+    # whose Jacobian branch differs between the fp32 kernel and the fp64 oracle
     for name, a, b in zip(("means", "quats", "scales", "opacity"), gl, leaves):
         ga, gb = a.grad.cpu()[same], b.grad[same]
-        assert frac_bad(ga, gb, 2e-4) < 5e-3, name
+        assert frac_bad(ga, gb, RTOL) < 5e-3, name
 
 
 # ---------------------------------------------------------------------------------------------
