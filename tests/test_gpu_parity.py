@@ -308,10 +308,16 @@ def test_full_backward_matches_oracle(D):
     out, alphas, _ = R._Blend.apply(gl[0], gl[1], gl[2], gl[3], bg.cuda(), st["geom"], st["offsets"],
                                     st["flatten_ids"], W, H)
     ((out * v_out.cuda()).sum() + (alphas * v_alpha.cuda()).sum()).backward()
-    # 1e-4 of scale against the fp64 oracle on identical inputs; the budget covers pixels where the
-    # fp32 kernel and the oracle disagree on an alpha / transmittance threshold (helpers docstring)
+    # The feature gradient is a sum of non-negative weights times v_out: well conditioned, 1e-4 of
+    # scale.  The geometry gradients are sums over pixels of terms that change sign across the
+    # Gaussian (d sigma / d mu is odd in the offset) and are individually larger than the sum: fp32
+    # accumulation in a different order (warp reductions + atomics vs the oracle's fp64) leaves
+    # ~1e-4 of the RESULT's scale although every term is accurate to ~1e-6, hence 2e-4 there; the
+    # counted budget covers pixels where the fp32 kernel and the oracle disagree on an alpha /
+    # transmittance threshold (tests/helpers.py).
     for name, a, b in zip(("means2d", "conics", "opac", "colors"), gl, leaves):
-        assert frac_bad(a.grad, b.grad, RTOL) < 2e-3, name
+        tol = RTOL if name == "colors" else 2e-4
+        assert frac_bad(a.grad, b.grad, tol) < 1e-3, name
         assert rel_err(a.grad, b.grad) < 2e-2, name
 
 

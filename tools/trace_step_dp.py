@@ -38,20 +38,23 @@ def step(i):
 for i in range(10): step(i)
 peer.synchronize(); torch.cuda.synchronize(); dist.barrier()
 acts = [ProfilerActivity.CUDA, ProfilerActivity.CPU]
-if rank == 0:
-    with profile(activities=acts) as prof:
-        for i in range(10, 14): step(i)
-        peer.synchronize(); torch.cuda.synchronize()
-    path = os.path.join(tempfile.gettempdir(), "trace_dp.json")
-    prof.export_chrome_trace(path)
-    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")]
-    ev.sort(key=lambda e: e["ts"])
-    t0 = ev[0]["ts"]
-    for e in ev:
-        name = e["name"].replace("void ", "").replace("(anonymous namespace)::", "")[:48]
-        print(f"{(e['ts']-t0)/1000:9.3f} ms  +{e['dur']/1000:7.3f}  s{e['args'].get('stream')}  {name}")
-else:
+# every rank profiles itself; rank 0 prints, all ranks also write gpurun_out/trace_dp{world}_rank{r}.txt
+with profile(activities=acts) as prof:
     for i in range(10, 14): step(i)
     peer.synchronize(); torch.cuda.synchronize()
+path = os.path.join(tempfile.gettempdir(), f"trace_dp_{rank}.json")
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")]
+ev.sort(key=lambda e: e["ts"])
+t0 = ev[0]["ts"]
+lines = []
+for e in ev:
+    name = e["name"].replace("void ", "").replace("(anonymous namespace)::", "")[:48]
+    lines.append(f"{(e['ts']-t0)/1000:9.3f} ms  +{e['dur']/1000:7.3f}  s{e['args'].get('stream')}  {name}")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", f"trace_dp{world}_rank{rank}.txt"), "w") as f:
+    f.write("\n".join(lines) + "\n")
+if rank == 0:
+    print("\n".join(lines))
 dist.barrier()
 dist.destroy_process_group()
