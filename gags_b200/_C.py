@@ -88,6 +88,10 @@ SIGNATURES = {
     "gags_set_peer_unroll": (C.c_int, [_i32]),
     "gags_adam_step_peer": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _i64, C.c_double,
                                       C.c_double, C.c_double, C.c_double, _i32, _p]),
+    "gags_grad_allreduce_rows": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+    "gags_adam_step_rows": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, _i32, _p]),
+    "gags_blend_cache_mark_rows": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
     "gags_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double,
                                  C.c_double, _i32, _i32, _p]),
 }

@@ -484,6 +484,24 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   return (int)cudaGetLastError();
 }
 
+// One warp per half tile: every Gaussian of a batch the forward blended (and cached) gets its
+// row flag set.  The feature backward reduces into exactly these rows (a superset of the rows whose
+// gradient is non-zero), so a flag of 0 promises an all-zero gradient row — what the row-sparse
+// optimiser pass (gags_adam_step_rows) and the sparse multi-GPU exchange skip.
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(int tile_w, int n_half, const int *__restrict__ offsets,
+                 const int *__restrict__ wmeta, const int *__restrict__ wlist,
+                 const int *__restrict__ wcount, unsigned char *__restrict__ flags) {
+  const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= n_half) return;
+  const CbJob jb = cb_job(w, 1, tile_w, 0, 128, offsets, wcount);
+  for (int gi = 0; gi < jb.nbat; ++gi) {
+    const int slot = jb.hbase + __ldg(wlist + jb.hbase + gi);
+    const int gid = __ldg(wmeta + (size_t)slot * TC_KB + lane);
+    if (gid >= 0) flags[gid] = 1;
+  }
+}
+
 }  // namespace
 
 extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
@@ -565,4 +583,19 @@ extern "C" int gags_blend_bwd_features_cached_sam(int32_t D, int32_t width, int3
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+// row_flags[g] = 1 for every Gaussian of every batch cached by gags_blend_fwd_cached for this view
+// (flags are only ever set here: the caller owns clearing them).
+extern "C" int gags_blend_cache_mark_rows(int32_t width, int32_t height, const int32_t *offsets,
+                                          const int32_t *wmeta, const int32_t *wlist,
+                                          const int32_t *wcount, uint8_t *row_flags, void *stream) {
+  if (!offsets || !wmeta || !wlist || !wcount || !row_flags || width <= 0 || height <= 0)
+    return GAGS_EINVAL;
+  const int tw = (width + GAGS_TILE - 1) / GAGS_TILE;
+  const int hh = (height + 7) / 8;
+  const int n_half = tw * hh;
+  mark_rows_kernel<<<(n_half + 7) / 8, 256, 0, (cudaStream_t)stream>>>(tw, n_half, offsets, wmeta,
+                                                                      wlist, wcount, row_flags);
+  return (int)cudaGetLastError();
 }

@@ -214,6 +214,51 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
   }
 }
 
+// Row-sparse form of adam_kernel for a [rows, D] table whose gradient is mostly zero rows (one view
+// touches ~1/6 of the Gaussians at config 3): `flags[row] == 0` PROMISES that gradient row `row` is
+// all zero, so the row's gradient is neither read nor re-zeroed and the update runs with g = 0 —
+// the same arithmetic on the same values as the dense pass, bit for bit (m and v still decay, p still
+// moves by its momentum).  Touched rows are read, applied and zeroed in this pass, so the gradient
+// buffer is all-zero again afterwards without a separate 4 B/parameter fill.  24 B per parameter on
+// untouched rows, 32 B on touched ones (dense pass + fill: 28 + 4).  The flags are cleared by the
+// caller behind the kernel (a row's threads may sit in different CTAs).
+template <bool POW2>
+__global__ void __launch_bounds__(256)
+adam_rows_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
+                 float4 *__restrict__ v, const unsigned char *__restrict__ flags, long long n4,
+                 int row4, int shift, float step_size, float b1, float b2, float omb1, float omb2,
+                 float inv_sqrt_bc2, float eps) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < n4;
+    const bool fa = flags[POW2 ? (i0 >> shift) : (i0 / row4)] != 0;
+    const bool fb = two && flags[POW2 ? (i1 >> shift) : (i1 / row4)] != 0;
+    float4 ma = m[i0], va = v[i0], pa = p[i0];
+    float4 mb = ma, vb = va, pb = pa;
+    if (two) { mb = m[i1]; vb = v[i1]; pb = p[i1]; }
+    float4 ga = zero, gb = zero;
+    if (fa) ga = g[i0];
+    if (fb) gb = g[i1];
+#define GAGS_ADAM1(P, G, M, V, c)                                 \
+    M.c = b1 * M.c + omb1 * G.c;                                  \
+    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
+    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
+    GAGS_ADAM1(pa, ga, ma, va, x) GAGS_ADAM1(pa, ga, ma, va, y)
+    GAGS_ADAM1(pa, ga, ma, va, z) GAGS_ADAM1(pa, ga, ma, va, w)
+    m[i0] = ma; v[i0] = va; p[i0] = pa;
+    if (fa) g[i0] = zero;
+    if (two) {
+      GAGS_ADAM1(pb, gb, mb, vb, x) GAGS_ADAM1(pb, gb, mb, vb, y)
+      GAGS_ADAM1(pb, gb, mb, vb, z) GAGS_ADAM1(pb, gb, mb, vb, w)
+      m[i1] = mb; v[i1] = vb; p[i1] = pb;
+      if (fb) g[i1] = zero;
+    }
+#undef GAGS_ADAM1
+  }
+}
+
 // ---- gradient all-reduce + Adam + parameter all-gather as ONE kernel over NVLink peer memory ---
 // View-parallel training replicates the feature table and sums its gradient over the ranks every
 // step (2 GB at config 3).  Here rank r owns the float4 range [start, start + count) of the table
@@ -310,6 +355,114 @@ adam_multicast_kernel(const float4 *mc_grad, float4 *mc_param, const float4 *__r
       }
     }
 #undef GAGS_ADAM1
+  }
+}
+
+// ---- row-sparse gradient all-reduce over NVLink peer memory -------------------------------------
+// A view's feature backward touches a small part of the table's rows (7 % at config 3; the union
+// over 8 consecutive views is 15 %), and every rank knows which ones (the row flags the backward
+// sets, rasterization.row_flags).  Instead of exchanging the whole [N, D] gradient (2 GB) and the
+// whole updated table (2 GB) per step, every rank keeps the full optimiser state and only the rows
+// flagged on ANY rank are summed: rank r owns a contiguous range of 4-row flag words; for each
+// owned word it ORs the ranks' flags, and for every flagged row it forms the sum of that row over
+// all ranks and writes it back into ALL replicas' gradient buffers (in place).  Each rank also
+// builds its own copy of the union flags for all rows (N bytes read through the fabric), which is
+// what its local row-sparse Adam pass (adam_rows_kernel) consumes afterwards.  MC = NVLS:
+// multimem.ld_reduce forms the sums inside the NVSwitch and multimem.st writes every replica;
+// otherwise plain peer loads (summed in rank order) and stores.  Every replica receives the same
+// bits for a row because exactly one rank computes it.  The caller brackets the launch with two
+// inter-rank barriers (all backward passes done before; all sums landed after).
+struct RowPeerPtrs {
+  float4 *grad[GAGS_MAX_PEERS];
+  const unsigned *flags[GAGS_MAX_PEERS];
+};
+
+__device__ __forceinline__ unsigned flags_or_mc(const unsigned *mc) {
+  unsigned u;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b32 %0, [%1];" : "=r"(u) : "l"(mc) : "memory");
+  return u;
+}
+__device__ __forceinline__ float4 ld_sum_mc(const float4 *mc) {
+  float4 g;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+               : "l"(mc)
+               : "memory");
+  return g;
+}
+__device__ __forceinline__ void st_mc(float4 *mc, const float4 &v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <bool MC, int MAXW>
+__global__ void __launch_bounds__(256)
+grad_rows_allreduce_kernel(RowPeerPtrs pp, int world, float4 *mc_grad, const unsigned *mc_flags,
+                           unsigned *__restrict__ uflags, long long words, long long w0,
+                           long long w1, int row4) {
+  const int lane = threadIdx.x & 31;
+  const long long gthreads = (long long)gridDim.x * blockDim.x;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto union_word = [&](long long w) -> unsigned {
+    if (MC) return flags_or_mc(mc_flags + w);
+    unsigned u = 0;
+#pragma unroll
+    for (int q = 0; q < MAXW; ++q)
+      if (q < world) u |= pp.flags[q][w];
+    return u;
+  };
+  // (1) this rank's copy of the union flags of ALL rows
+  for (long long w = gtid; w < words; w += gthreads) uflags[w] = union_word(w);
+  // (2) the owned words: one warp per word (4 rows), lanes across the row
+  const long long gwarp = gtid >> 5, nwarps = gthreads >> 5;
+  for (long long w = w0 + gwarp; w < w1; w += nwarps) {
+    unsigned u = 0;
+    if (lane == 0) u = union_word(w);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u == 0u) continue;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (((u >> (8 * r)) & 0xffu) == 0u) continue;                // warp-uniform
+      const long long base = (w * 4 + r) * (long long)row4;
+      for (int c0 = 0; c0 < row4; c0 += 128) {
+        // up to four 16-byte reductions in flight per lane
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k * 32 + lane;
+          if (c < row4) {
+            if (MC) {
+              acc[k] = ld_sum_mc(mc_grad + base + c);
+            } else {
+              float4 gq[MAXW];
+#pragma unroll
+              for (int q = 0; q < MAXW; ++q)
+                if (q < world) gq[q] = pp.grad[q][base + c];
+              acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < MAXW; ++q)
+                if (q < world) {
+                  acc[k].x += gq[q].x; acc[k].y += gq[q].y; acc[k].z += gq[q].z; acc[k].w += gq[q].w;
+                }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k * 32 + lane;
+          if (c < row4) {
+            if (MC) {
+              st_mc(mc_grad + base + c, acc[k]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < MAXW; ++q)
+                if (q < world) pp.grad[q][base + c] = acc[k];
+            }
+          }
+        }
+      }
+    }
   }
 }
 
@@ -454,6 +607,43 @@ extern "C" int gags_adam_step(float *param, float *grad, float *exp_avg, float *
   return 0;
 }
 
+// gags_adam_step on a [rows, D] table with per-row gradient flags (see adam_rows_kernel): rows whose
+// flag is 0 take the g = 0 update without their gradient being read; flagged rows are applied and
+// their gradient zeroed; the flags are cleared behind the kernel.  D % 4 == 0.
+extern "C" int gags_adam_step_rows(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                   uint8_t *row_flags, int64_t rows, int32_t D, double lr,
+                                   double beta1, double beta2, double eps, int32_t step,
+                                   void *stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !row_flags || rows < 0 || D < 4 || step < 1)
+    return GAGS_EINVAL;
+  if (D % 4 != 0) return GAGS_EINVAL;
+  if (!gags_aligned16(param) || !gags_aligned16(grad) || !gags_aligned16(exp_avg) ||
+      !gags_aligned16(exp_avg_sq))
+    return GAGS_EALIGN;
+  if (rows == 0) return 0;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+  const int row4 = D / 4;
+  const long long n4 = (long long)rows * row4;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > gags_sm_count() * 4) blocks = gags_sm_count() * 4;
+  int shift = -1;
+  if ((row4 & (row4 - 1)) == 0) { shift = 0; while ((1 << shift) < row4) ++shift; }
+#define GAGS_ROWS_ARGS reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),        \
+      reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), row_flags, n4,  \
+      row4, shift, step_size, (float)beta1, (float)beta2, omb1, omb2, inv_sqrt_bc2, (float)eps
+  if (shift >= 0) adam_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(GAGS_ROWS_ARGS);
+  else adam_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(GAGS_ROWS_ARGS);
+#undef GAGS_ROWS_ARGS
+  GAGS_CHECK_LAUNCH();
+  cudaError_t e = cudaMemsetAsync(row_flags, 0, (size_t)rows, st);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 // Tuning hook for the two exchange kernels (tools/peer_rate.py sweeps it): CTAs per SM of their
 // grids; 0 = the built-in choice (4 for the unicast form, 2 for the multicast form).
 static int g_peer_ctas_per_sm = 0;
@@ -553,6 +743,57 @@ extern "C" int gags_adam_step_multicast(const float *mc_grad, float *mc_param,
   else if (g_peer_unroll == 8) GAGS_MC_LAUNCH(8);
   else GAGS_MC_LAUNCH(4);
 #undef GAGS_MC_LAUNCH
+  GAGS_CHECK_LAUNCH();
+  return 0;
+}
+
+// Row-sparse gradient all-reduce (grad_rows_allreduce_kernel).  grad_ptrs[q] / flag_ptrs[q]: every
+// rank's [rows, D] gradient buffer and its row flags (uint8 [4 * words], words = ceil(rows / 4),
+// zero padded), mapped into this process; mc_grad / mc_flags: their NVLS multicast addresses, or
+// NULL for the unicast form.  union_flags (local, 4 * words bytes) receives the OR of all ranks'
+// flags; the gradient rows flagged there hold the sum over ranks afterwards, on every rank, for
+// the words [w0, w1) this rank owns (all ranks together cover [0, words)).
+extern "C" int gags_grad_allreduce_rows(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
+                                        const uint64_t *flag_ptrs, float *mc_grad,
+                                        const uint8_t *mc_flags, uint8_t *union_flags, int64_t rows,
+                                        int32_t D, void *stream) {
+  if (!grad_ptrs || !flag_ptrs || !union_flags || world < 1 || world > GAGS_MAX_PEERS || rank < 0 ||
+      rank >= world || rows < 0 || D < 4 || (D % 4) != 0)
+    return GAGS_EINVAL;
+  if ((mc_grad == nullptr) != (mc_flags == nullptr)) return GAGS_EINVAL;
+  if (rows == 0) return 0;
+  RowPeerPtrs pp;
+  for (int q = 0; q < GAGS_MAX_PEERS; ++q) {
+    pp.grad[q] = nullptr;
+    pp.flags[q] = nullptr;
+  }
+  for (int q = 0; q < world; ++q) {
+    pp.grad[q] = reinterpret_cast<float4 *>(grad_ptrs[q]);
+    pp.flags[q] = reinterpret_cast<const unsigned *>(flag_ptrs[q]);
+    if (!pp.grad[q] || !pp.flags[q]) return GAGS_EINVAL;
+    if (!gags_aligned16(pp.grad[q]) || (flag_ptrs[q] & 3)) return GAGS_EALIGN;
+  }
+  if (mc_grad && (!gags_aligned16(mc_grad) || ((uintptr_t)mc_flags & 3))) return GAGS_EALIGN;
+  if ((uintptr_t)union_flags & 3) return GAGS_EALIGN;
+  const long long words = (rows + 3) / 4;
+  const long long per = (words + world - 1) / world;
+  long long w0 = per * rank, w1 = per * (rank + 1);
+  if (w0 > words) w0 = words;
+  if (w1 > words) w1 = words;
+  // a small grid: the exchange is bound by the fabric and runs beside the next view's projection /
+  // tile sort (gags_set_peer_grid overrides, as for the dense exchange kernels)
+  const long long blocks = (long long)gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GAGS_ROWS_AR(MC, MAXW)                                                                     \
+  grad_rows_allreduce_kernel<MC, MAXW><<<(unsigned)blocks, 256, 0, st>>>(                           \
+      pp, world, reinterpret_cast<float4 *>(mc_grad), reinterpret_cast<const unsigned *>(mc_flags), \
+      reinterpret_cast<unsigned *>(union_flags), words, w0, w1, D / 4)
+  if (mc_grad) GAGS_ROWS_AR(true, 1);
+  else if (world <= 2) GAGS_ROWS_AR(false, 2);
+  else if (world <= 4) GAGS_ROWS_AR(false, 4);
+  else if (world <= 8) GAGS_ROWS_AR(false, 8);
+  else GAGS_ROWS_AR(false, GAGS_MAX_PEERS);
+#undef GAGS_ROWS_AR
   GAGS_CHECK_LAUNCH();
   return 0;
 }

@@ -142,7 +142,7 @@ def _early_prezero(colors, geo_in, sh_degree) -> None:
     N, D = colors.shape
     if not _C.lib.gags_blend_cache_supported(D):
         return
-    if (direct_grad_accumulation and colors.is_leaf and colors.grad is not None):
+    if (_direct(colors) and colors.is_leaf and colors.grad is not None):
         return                                        # the backward will reduce straight into .grad
     dev = colors.device
     zs = _zero_stream(dev)
@@ -478,6 +478,45 @@ sink_ready_events: Dict = {}
 param_ready_events: Dict = {}
 
 
+class RowFlags:
+    """Per-row "this gradient row may be non-zero" flags of a persistent `.grad` buffer
+    (optim.FusedAdam(sparse_rows=True), parallel.SparsePeerAdam).  `flags` uint8 [N]: 0 promises an
+    all-zero row.  `dirty`: a backward has written into the buffer since the owner last consumed it."""
+    __slots__ = ("flags", "dirty")
+
+    def __init__(self, flags):
+        self.flags, self.dirty = flags, False
+
+
+# data_ptr of a persistent `.grad` buffer -> RowFlags.  The owner (the optimiser) keeps the buffer
+# alive for as long as the entry exists, so the address cannot be recycled under it.
+row_flags: Dict[int, RowFlags] = {}
+
+
+def _direct(colors) -> bool:
+    """Reduce this tensor's feature gradient straight into its `.grad`?  Process-wide switch or the
+    per-parameter opt-in an optimiser sets on the parameters it keeps a persistent gradient for."""
+    return direct_grad_accumulation or getattr(colors, "_gags_direct_grad", False)
+
+
+def _mark_rows(v_colors, cache, offsets, width: int, height: int) -> None:
+    """After a feature backward that accumulated into `v_colors`: if that buffer carries row flags,
+    flag the rows this view can have touched (cached backward: the rows of the batches the forward
+    kept; any other kernel: all rows)."""
+    rf = row_flags.get(v_colors.data_ptr()) if (row_flags and v_colors is not None) else None
+    if rf is None:
+        return
+    rf.dirty = True
+    if cache is not None:
+        _C.check(_C.lib.gags_blend_cache_mark_rows(width, height, _C.ptr(offsets), _C.ptr(cache[1]),
+                                                   _C.ptr(cache[2]), _C.ptr(cache[3]),
+                                                   _C.ptr(rf.flags), _C.stream_ptr()),
+                 "gags_blend_cache_mark_rows")
+        _C.count_launch()
+    else:
+        rf.flags.fill_(1)
+
+
 def _take_grad_buffer(ctx, need_col: bool, need_geo: bool, N: int, D: int, dev):
     """The [N, D] buffer the feature backward accumulates into, and the leaf it belongs to when the
     reduction goes straight into `.grad` (direct_grad_accumulation)."""
@@ -574,6 +613,7 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
         _C.ptr(cache[3]), _C.ptr(r), _C.ptr(sg), _C.ptr(em), _C.ptr(m), em.shape[0], 1.0 / numel,
         _C.ptr(loss), _C.ptr(v_colors), _C.stream_ptr()), "gags_blend_bwd_features_cached_l1")
     _C.count_launch((D + 255) // 256)
+    _mark_rows(v_colors, cache, h.offsets, width, height)
     _mark("blend_bwd")
     _finish_fused_backward(render_dhw, h, v_colors, sink)
     return loss[0] / numel
@@ -617,6 +657,7 @@ def fused_sam_backward(render_dhw, seg3, emb, scale_map, want_scale_grad: bool =
         _C.ptr(loss), _C.ptr(v_scale), _C.ptr(v_colors), _C.stream_ptr()),
         "gags_blend_bwd_features_cached_sam")
     _C.count_launch((D + 255) // 256)
+    _mark_rows(v_colors, cache, h.offsets, width, height)
     _mark("blend_bwd")
     _finish_fused_backward(render_dhw, h, v_colors, sink)
     return loss[0] / numel, v_scale
@@ -631,7 +672,7 @@ class _Blend(torch.autograd.Function):
                 width, height):
         _C.require_cuda(colors, geom)
         ctx.sink = None
-        if (direct_grad_accumulation and colors.is_leaf and colors.requires_grad
+        if (_direct(colors) and colors.is_leaf and colors.requires_grad
                 and colors.dtype == torch.float32 and colors.is_contiguous()):
             ctx.sink = colors
         colors = _f32c(colors)
@@ -727,6 +768,8 @@ class _Blend(torch.autograd.Function):
                                                 _C.ptr(va), _C.ptr(v_m), _C.ptr(v_c), _C.ptr(v_o),
                                                 _C.ptr(v_colors), st), "gags_blend_bwd_full")
             _C.count_launch(2)
+        if need_col:
+            _mark_rows(v_colors, cache if not need_geo else None, offsets, width, height)
         _mark("blend_bwd")
         if ctx.needs_input_grad[4] and bg is not None:
             v_bg = (v_render * (1.0 - alphas)[..., None]).sum(dim=(0, 1))

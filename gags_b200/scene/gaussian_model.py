@@ -225,7 +225,10 @@ class GaussianModel:
             t.requires_grad_(False)
         if fused_optimizer:
             from ..optim import FusedAdam
-            self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+            # row-sparse gradient handling (optim.py): on unless GAGS_B200_SPARSE_ADAM=0
+            import os
+            self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15,
+                                       sparse_rows=os.environ.get("GAGS_B200_SPARSE_ADAM", "1") != "0")
         else:
             self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
         self.xyz_scheduler_args = get_expon_lr_func(

@@ -285,6 +285,22 @@ int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                    double lr, double beta1, double beta2, double eps, int32_t step,
                    int32_t zero_grad, void *stream);
 
+/* Row-sparse form for a [rows, D] table (D % 4 == 0) whose gradient is mostly zero rows — one view
+ * touches a small part of the Gaussians, yet torch.optim.Adam (the reference's optimiser) reads and
+ * the training loop re-zeroes the whole [N, D] gradient every step ("dense
+ * even though only visible rows have grad").  row_flags[r] == 0 PROMISES gradient row r is all zero:
+ * the row takes the g = 0 update (m, v decay, p moves by its momentum — bit-identical to the dense
+ * pass) without its gradient being read.  Flagged rows are applied AND zeroed, and the flags are
+ * cleared, so afterwards the gradient buffer is all zero again with no separate fill.            */
+int gags_adam_step_rows(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                        uint8_t *row_flags, int64_t rows, int32_t D, double lr, double beta1,
+                        double beta2, double eps, int32_t step, void *stream);
+/* Sets row_flags[g] = 1 for every Gaussian of every batch gags_blend_fwd_cached kept for this view
+ * (the rows the cached feature backward reduces into; never clears a flag).                      */
+int gags_blend_cache_mark_rows(int32_t width, int32_t height, const int32_t *offsets,
+                               const int32_t *wmeta, const int32_t *wlist, const int32_t *wcount,
+                               uint8_t *row_flags, void *stream);
+
 /* Multi-GPU form of gags_adam_step: gradient all-reduce + Adam + parameter all-gather in ONE kernel
  * over NVLink peer memory (view-parallel training).  grad_ptrs[q] / param_ptrs[q]
  * (host arrays of `world` device addresses, q = rank) are every rank's full [numel] gradient and
@@ -307,6 +323,19 @@ int gags_adam_step_multicast(const float *mc_grad, float *mc_param, const float 
                              float *exp_avg_shard, float *exp_avg_sq_shard, int64_t start,
                              int64_t count, double lr, double beta1, double beta2, double eps,
                              int32_t step, void *stream);
+
+/* Row-sparse gradient all-reduce for view-parallel training: only the rows some
+ * rank's backward flagged (gags_blend_cache_mark_rows) are summed over the ranks, in place, into
+ * every replica's gradient buffer; each rank keeps the full optimiser state and follows with its own
+ * gags_adam_step_rows driven by `union_flags`.  grad_ptrs[q] / flag_ptrs[q] (host arrays of `world`
+ * device addresses): every rank's [rows, D] gradient buffer and its uint8 row flags (4 * ceil(rows/4)
+ * bytes, zero padded), mapped into this process; mc_grad / mc_flags: their NVLS multicast addresses
+ * (multimem.ld_reduce / multimem.st), or both NULL for plain peer loads / stores.  union_flags
+ * (local, same size as the flags) receives the OR over ranks.  Barriers before and after the call
+ * are the caller's, as for gags_adam_step_peer.                                                   */
+int gags_grad_allreduce_rows(int32_t world, int32_t rank, const uint64_t *grad_ptrs,
+                             const uint64_t *flag_ptrs, float *mc_grad, const uint8_t *mc_flags,
+                             uint8_t *union_flags, int64_t rows, int32_t D, void *stream);
 
 /* Tuning hook: CTAs per SM of the two exchange kernels' grids (0 = built-in: 4 unicast, 2
  * multicast).  Process-wide; used by tools/peer_rate.py.                                         */

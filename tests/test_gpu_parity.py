@@ -308,16 +308,17 @@ def test_full_backward_matches_oracle(D):
     out, alphas, _ = R._Blend.apply(gl[0], gl[1], gl[2], gl[3], bg.cuda(), st["geom"], st["offsets"],
                                     st["flatten_ids"], W, H)
     ((out * v_out.cuda()).sum() + (alphas * v_alpha.cuda()).sum()).backward()
-    # The feature gradient is a sum of non-negative weights times v_out: well conditioned, 1e-4 of
-    # scale.  The geometry gradients are sums over pixels of terms that change sign across the
-    # Gaussian (d sigma / d mu is odd in the offset) and are individually larger than the sum: fp32
-    # accumulation in a different order (warp reductions + atomics vs the oracle's fp64) leaves
-    # ~1e-4 of the RESULT's scale although every term is accurate to ~1e-6, hence 2e-4 there; the
-    # counted budget covers pixels where the fp32 kernel and the oracle disagree on an alpha /
-    # transmittance threshold (tests/helpers.py).
+    # Measured error profile against the fp64 oracle fed identical inputs (tools/diag_full_bwd.py, B200):
+    # every element of all four gradients is within 2e-4 of its tensor's scale, at every D; at 1e-4
+    # between 0 and 2 elements of a tensor are over (max 1.7e-4).  The full backward walks each
+    # pixel's list back to front and recovers the transmittance by repeated division, T /= (1 - a),
+    # as gsplat's kernel does: in fp32 that accumulates ~1e-7 per step over up to
+    # ~10^2 steps, and the geometry gradients are sums of terms of both signs that are individually
+    # larger than the result.  Hence 2e-4 (the 1e-3 budget admits no outlier below 1000 elements and
+    # bounds them above; rel_err caps what an outlier may be), while the feature-only kernels, which reuse the forward's weights, hold
+    # 1e-4 (test_tensor_core_feature_backward_matches_simt_and_oracle).
     for name, a, b in zip(("means2d", "conics", "opac", "colors"), gl, leaves):
-        tol = RTOL if name == "colors" else 2e-4
-        assert frac_bad(a.grad, b.grad, tol) < 1e-3, name
+        assert frac_bad(a.grad, b.grad, 2e-4) < 1e-3, name
         assert rel_err(a.grad, b.grad) < 2e-2, name
 
 
@@ -765,3 +766,123 @@ def test_zero_fill_and_guarded_sort_argument_checks():
                                                 _C.stream_ptr()) != 0
     assert _C.lib.gags_adam_step_peer(0, 0, None, None, None, None, 0, 0, 1e-3, 0.9, 0.999, 1e-8,
                                       1, _C.stream_ptr()) != 0
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sparse optimiser pass (optim.FusedAdam(sparse_rows=True), csrc/train_ops.cu adam_rows_kernel)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,D", [(5000, 256), (777, 12), (1, 4), (3001, 64)])
+def test_adam_rows_is_bit_identical_to_dense(rows, D):
+    """gags_adam_step_rows == gags_adam_step on a gradient whose unflagged rows are zero: same bits
+    in p / m / v, flagged rows re-zeroed, flags cleared (power-of-two and odd row lengths)."""
+    from gags_b200 import _C
+    g = torch.Generator().manual_seed(rows + D)
+    p0 = torch.randn(rows, D, generator=g).cuda()
+    m0 = (0.1 * torch.randn(rows, D, generator=g)).cuda()
+    v0 = (0.01 * torch.rand(rows, D, generator=g)).cuda()
+    flags = (torch.rand(rows, generator=g) < 0.2).to(torch.uint8).cuda()
+    gr = torch.randn(rows, D, generator=g).cuda() * flags[:, None].float()
+    gr[flags.bool().nonzero()[:1]] = 0.0                 # a flagged row may still be all zero
+    outs = []
+    for sparse in (False, True):
+        p, m, v, gg, f = p0.clone(), m0.clone(), v0.clone(), gr.clone(), flags.clone()
+        for step in (1, 2):
+            if sparse:
+                _C.check(_C.lib.gags_adam_step_rows(p.data_ptr(), gg.data_ptr(), m.data_ptr(),
+                                                    v.data_ptr(), f.data_ptr(), rows, D, 1e-3, 0.9,
+                                                    0.999, 1e-15, step, _C.stream_ptr()))
+            else:
+                _C.check(_C.lib.gags_adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(),
+                                               v.data_ptr(), rows * D, 1e-3, 0.9, 0.999, 1e-15,
+                                               step, 1, _C.stream_ptr()))
+            torch.cuda.synchronize()
+            assert float(gg.abs().max()) == 0.0          # second step: every row takes g = 0
+            if sparse:
+                assert int(f.sum()) == 0
+        outs.append((p, m, v))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert _C.lib.gags_adam_step_rows(None, None, None, None, None, 4, 4, 1e-3, 0.9, 0.999, 1e-8, 1,
+                                      _C.stream_ptr()) != 0
+    assert _C.lib.gags_adam_step_rows(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                      f.data_ptr(), rows, 6, 1e-3, 0.9, 0.999, 1e-8, 1,
+                                      _C.stream_ptr()) != 0      # D % 4 != 0
+
+
+@pytest.mark.parametrize("D,autograd_loss", [(64, False), (256, False), (128, True), (16, False)])
+def test_sparse_rows_training_equals_dense_adam(D, autograd_loss):
+    """Five optimiser steps over different views with FusedAdam(sparse_rows=True): persistent .grad,
+    row flags set by the backward, g = 0 update on unflagged rows.  Every step is checked against the
+    dense kernel run on copies of (p, g, m, v) taken just before it: bit-identical parameters and
+    moments (so no row with a gradient was left unflagged), flagged rows re-zeroed, flags cleared;
+    zero_grad(set_to_none=True) — the train.py loop — keeps the buffer.  D = 16 takes the non-cached
+    kernels (every row flagged), autograd_loss the autograd route into the sink."""
+    from gags_b200 import _C, rasterization as R
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.optim import FusedAdam
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_backward_fused, l1_loss_segmap_fused
+    dev = torch.device("cuda:0")
+    H, W = 72, 112
+    scene = make_scene(6000, H, W, D, seed=21, n_views=8, sigma_px_median=1.5)
+    g = torch.Generator().manual_seed(5)
+    seg = torch.randint(0, 9, (H, W), generator=g, dtype=torch.int32).to(dev)
+    emb = (0.2 * torch.randn(9, D, generator=g)).to(dev)
+    bg = torch.zeros(3, device=dev)
+    pc = GaussianModel(3, device=dev)
+    pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                           scene.features_dc, scene.features_rest, scene.semantic_feature)
+    pc.training_setup(OptimizationParams(), fused_optimizer=True)
+    p = pc._semantic_feature
+    opt = pc.optimizer = FusedAdam([{"params": [p], "lr": 1e-2}], lr=1e-2, eps=1e-15,
+                                   sparse_rows=True)
+    fracs = []
+    for it in range(5):
+        for v in ((it, it + 3) if it == 2 else (it,)):           # one step accumulates two views
+            pkg = render(scene.cameras[v % 8].to(dev), pc, None, bg)
+            if autograd_loss:
+                l1_loss_segmap_fused(pkg["render"], seg, emb).backward()
+            else:
+                l1_backward_fused(pkg["render"], seg, emb)
+        rows = opt._rows.get(id(p))
+        if it > 0:
+            assert rows is not None and rows[0].data_ptr() == p.grad.data_ptr()
+            nz = p.grad.abs().amax(dim=1) > 0
+            assert int(nz.sum()) > 0
+            assert bool((rows[1].flags.bool() | ~nz).all())       # flagged rows cover the gradient
+            fracs.append(float(rows[1].flags.float().mean()))
+        st = opt.state[p]
+        have = len(st) > 0
+        rp, rg = p.detach().clone(), p.grad.clone()
+        rm = st["exp_avg"].clone() if have else torch.zeros_like(rp)
+        rv = st["exp_avg_sq"].clone() if have else torch.zeros_like(rp)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        _C.check(_C.lib.gags_adam_step(rp.data_ptr(), rg.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                       rp.numel(), 1e-2, 0.9, 0.999, 1e-15, it + 1, 0,
+                                       _C.stream_ptr()))
+        torch.cuda.synchronize()
+        st = opt.state[p]
+        assert torch.equal(p.detach(), rp)
+        assert torch.equal(st["exp_avg"], rm) and torch.equal(st["exp_avg_sq"], rv)
+        assert p.grad is not None and float(p.grad.abs().max()) == 0.0
+        assert int(opt._rows[id(p)][1].flags.sum()) == 0
+    if D > 32:
+        assert max(fracs) < 1.0                                   # the cached route flags a subset
+    else:
+        assert min(fracs) == 1.0
+    # a gradient that arrives through autograd's own accumulation flags every row
+    (p * 2.0).sum().backward()
+    assert int(opt._rows[id(p)][1].flags.sum()) == p.shape[0]
+    # a backward that is never applied is dropped by zero_grad
+    opt.zero_grad(set_to_none=True)
+    assert float(p.grad.abs().max()) == 0.0 and int(opt._rows[id(p)][1].flags.sum()) == 0
+    # .grad replaced from outside: adopted again at the next step
+    p.grad = None
+    pkg = render(scene.cameras[0].to(dev), pc, None, bg)
+    l1_backward_fused(pkg["render"], seg, emb)
+    opt.step()
+    assert opt._rows[id(p)][0].data_ptr() == p.grad.data_ptr() and float(p.grad.abs().max()) == 0.0
+    assert not R.direct_grad_accumulation
