@@ -66,6 +66,8 @@ SIGNATURES = {
     "gags_blend_cache_slots": (_i64, [_i64, _i32]),
     "gags_blend_fwd_cached": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                         _p, _p]),
+    "gags_blend_fwd_weights": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gags_blend_fwd_from_cache": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gags_blend_bwd_features_cached": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gags_blend_bwd_features_cached_l1": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                                                     _p, _i32, _f, _p, _p, _p]),
@@ -89,6 +91,9 @@ SIGNATURES = {
     "gags_adam_step_peer": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _i64, C.c_double,
                                       C.c_double, C.c_double, C.c_double, _i32, _p]),
     "gags_grad_allreduce_rows": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+    "gags_adam_step_consts": (C.c_int, [C.c_double, C.c_double, C.c_double, _i32, _p]),
+    "gags_adam_lazy_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, C.c_double,
+                                      C.c_double, C.c_double, _i32, _p]),
     "gags_adam_step_rows": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, C.c_double, C.c_double,
                                       C.c_double, C.c_double, _i32, _p]),
     "gags_blend_cache_mark_rows": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),

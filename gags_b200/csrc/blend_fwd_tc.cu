@@ -52,12 +52,20 @@ extern "C" int gags_debug_timeline(long long *host_dst, int n) {
 
 // 2 = one thread per pixel evaluates alpha and the chain (round-1 kernel); 3 = front / chain split.
 int g_fwd_variant = 3;
+extern int g_gags_blend_impl;   // api.cu: 0 auto, 1 SIMT only, 2 tensor cores required
 
 namespace {
 
 constexpr int KB = TC_KB;
 constexpr int RING = TC_RING;
 constexpr int TC_THREADS = 448;   // 13 role warps + the weight-tile store warp
+// the weights pass (MODE 1) has no converters, no MMA issuer and no epilogue: 4 chain + 4 front warps
+// + the store warp, three CTAs per SM
+template <int MODE> struct TcCfg {
+  static constexpr int THREADS = MODE == 1 ? 288 : TC_THREADS;
+  static constexpr int MINB = MODE == 1 ? 3 : 2;
+  static constexpr int NCW = MODE == 2 ? 8 : 4;      // converter warps (MODE 2: the chain warps too)
+};
 
 struct TcCtl {
   uint64_t list[2], full[2], free_[2], sdone[2], afull[2];
@@ -92,8 +100,14 @@ struct TcLayout {
 // two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
 static_assert(TcLayout<4>::BYTES <= (233472 / 2 - 1024), "forward TC kernel must fit twice per SM");
 
-template <int NATOM, bool V3>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// MODE 0: the whole forward in one pass.  The two-pass form splits it at the weight-tile cache:
+// MODE 1 (weights pass): scan + cull + alpha + transmittance chain only — writes alphas / last_ids,
+//         the cached weight tiles and the batch lists, touches no feature and no raster; what it
+//         blends is therefore known (gags_blend_cache_mark_rows) BEFORE any feature row is read.
+// MODE 2 (blend pass): render = cached weights x features — the front / chain warps are replaced
+//         by one producer thread that lands each cached 16 KB tile in the A stage with a bulk copy.
+template <int NATOM, bool V3, int MODE>
+__global__ void __launch_bounds__(TcCfg<MODE>::THREADS, TcCfg<MODE>::MINB)
 blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, int D, int ch0,
              int nch, const float *__restrict__ bg, int W, int H, int tile_w,
              const int *__restrict__ offsets, const int *__restrict__ ids,
@@ -116,7 +130,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   const int s = offsets[tile], e = offsets[tile + 1];
   // weight-tile cache (training only): batch i of this half tile lives in slot hbase + i, see
   // gags_blend_cache_slots() for the closed-form, scan-free slot bound
-  const bool cache = wcache != nullptr;
+  const bool cache = MODE != 2 && wcache != nullptr;
   const int cbase = (s >> 5) + tile;
   const int hbase = 2 * cbase + (int)(blockIdx.y & 1) * ((e >> 5) + tile + 1 - cbase);
 #ifdef GAGS_TC_TIMING
@@ -131,8 +145,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
 
   if (tid == 0) {
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&ctl.list[k], 4);                  // scanner warps
-      mbar_init(&ctl.full[k], 8);                  // pixel + converter warps
+      mbar_init(&ctl.list[k], MODE == 2 ? 1 : 4);  // scanner warps (MODE 2: the tile producer)
+      mbar_init(&ctl.full[k], MODE == 2 ? TcCfg<MODE>::NCW + 1 : 8);  // pixel + converter warps (MODE 2: producer + conv.)
       mbar_init(&ctl.free_[k], 1);                 // MMA commit: stage's B tile and records reusable
       mbar_init(&ctl.sdone[k], 1);                 // training: the tile store has read the A stage
       mbar_init(&ctl.afull[k], 4);                 // training: pixel warps -> store warp, A tile written
@@ -150,12 +164,14 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     const bool nzw = __any_sync(0xffffffffu, b != 0.f);
     if (lane == 0) ctl.bg_nonzero[warp] = nzw ? 1 : 0;
   }
-  if (warp == 12) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  if constexpr (MODE != 1) {
+    if (warp == 12) tmem_alloc<L::TCOLS>(&ctl.tmem_base);
+  }
   // v3: the front warps start walking the tile list right away — the first scan round is two
   // dependent global loads (ids -> geometry) of pure latency, and nothing it touches (the survivor
   // ring, named barrier 1) depends on the barrier / TMEM set-up the other warps are doing
   TcScanner sc;
-  if (V3 && warp >= 4 && warp < 8) {
+  if (V3 && MODE != 2 && warp >= 4 && warp < 8) {
     sc.init(geom, ids, s, e, (float)x0 + 0.5f, (float)y0 + 0.5f, rg0, rg1, rgid, ctl.wcnt,
             tid - 128);
     if (sc.scan < e) sc.issue();
@@ -170,7 +186,42 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   tc_fence_after();
   const uint32_t tb = ctl.tmem_base;
 
-  if (V3 && warp < 4) {
+  if (MODE == 2 && warp < 4) {
+    // final transmittance of this half tile's pixels, for the background term of the epilogue
+    const int dx = ((warp & 1) << 3) + (lane & 7), dy = ((warp >> 1) << 2) + (lane >> 3);
+    const int pxi = x0 + dx, pyi = y0 + dy;
+    ctl.Tfin[tid] = (pxi < W && pyi < H) ? 1.f - alphas[(size_t)pyi * W + pxi] : 0.f;
+  }
+  if (MODE == 2 && warp >= 4 && warp < 8) {
+    // ======================= blend pass: cached-tile producer (warp 4) =============================
+    if (warp == 4) {
+      const int nbat = wcount[blockIdx.y * gridDim.x + blockIdx.x];
+      for (int i = 0; i <= nbat; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+        int gid = -1;
+        size_t slot = 0;
+        if (i < nbat) {
+          slot = (size_t)hbase + (size_t)__ldg(wlist + hbase + i);
+          gid = __ldg(wmeta + slot * KB + lane);
+        }
+        ctl.gid[st][lane] = gid;
+        const int nb = __popc(__ballot_sync(0xffffffffu, gid >= 0));
+        if (lane == 0) ctl.gcount[st] = nb;
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ctl.list[st]);
+          if (i < nbat) {
+            mbar_expect_tx(&ctl.full[st], 16384u);
+            bulk_g2s(sA + st * 16384, wcache + slot * 16384, 16384u, &ctl.full[st]);
+          }
+        }
+        __syncwarp();
+      }
+      // every MMA issued has completed once the last batch's commit has arrived
+      if (nbat > 0) mbar_wait_bounded(&ctl.free_[(nbat - 1) & 1], ((nbat - 1) >> 1) & 1);
+    }
+  } else if (V3 && MODE != 2 && warp < 4) {
     // ======================= v3 chain warps: one thread per pixel ==================================
     // reads the 32 alphas the front warp of the same 8x4 block left in this pixel's A-tile row,
     // runs the transmittance chain and overwrites the row with the bf16 [hi | lo] weights
@@ -249,8 +300,8 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       alphas[pix] = want_last ? 1.f - ps.T : ps.T;
       if (want_last) last_ids[pix] = ps.last;
     }
-    if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
-  } else if (V3 && warp < 8) {
+    if (MODE != 1 && i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
+  } else if (V3 && MODE != 2 && warp < 8) {
     // ======================= v3 front warps: scanner + alpha evaluation ============================
     // lane = Gaussian of the batch: the record stays in registers and the warp evaluates the 32
     // alphas of ITS 8x4 pixel block (front warp w <-> chain warp w), all independent
@@ -271,7 +322,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (!sc.pending && nb > 0 && (sc.queued() - nb) < KB && sc.scan < e) sc.issue();
       // stage reuse: the MMA of batch i-2 has read A / B / gid, and (training) its tile has left A
       if (i >= 2) {
-        mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
+        if (MODE != 1) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
         if (cache) mbar_wait_bounded(&ctl.sdone[st], ((i >> 1) - 1) & 1);
       }
       // this lane's Gaussian of the batch, straight from the survivor ring
@@ -303,7 +354,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (nb == 0) break;
       sc.qhead += nb;
     }
-  } else if (warp < 4) {
+  } else if (MODE != 2 && warp < 4) {
     // ======================= pixel warps: one thread per pixel =====================================
     const int pw = warp;
     const int dx = ((pw & 1) << 3) + (lane & 7), dy = ((pw >> 1) << 2) + (lane >> 3);
@@ -377,7 +428,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     }
     // every MMA issued has completed once the last batch's commit has arrived
     if (i > 0) mbar_wait_bounded(&ctl.free_[(i - 1) & 1], ((i - 1) >> 1) & 1);
-  } else if (warp < 8) {
+  } else if (MODE != 2 && warp < 8) {
     // ======================= scanner warps =========================================================
     const int p = tid - 128;
     TcScanner sc;
@@ -417,10 +468,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (nb == 0) break;
       sc.qhead += nb;
     }
-  } else if (warp < 12) {
+  } else if (MODE != 1 && warp < 12) {
     // ======================= converter warps =======================================================
-    // warp cw owns batch rows [8 cw, 8 cw + 8); lane owns channels [8 lane, 8 lane + 8).
-    const int cw = warp - 8;
+    // warp cw owns batch rows [ROWS cw, ROWS cw + ROWS), ROWS = 32 / NCW; lane owns channels
+    // [8 lane, 8 lane + 8).  (MODE 2: the four chain warps convert as well, NCW = 8.)
+    {
+    constexpr int NCW = TcCfg<MODE>::NCW, ROWS = 32 / NCW, RND = ROWS / 4;
+    const int cw = warp >= 8 ? warp - 8 : warp + 4;
     const int n0 = lane * 8;
     const bool chan_ok = n0 < nch;
     const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
@@ -461,7 +515,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     header(0, nb, skipb);
     if (nb > 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) load_row(0, nb, skipb, cw * 8 + j, v[j]);
+      for (int j = 0; j < 4; ++j) load_row(0, nb, skipb, cw * ROWS + j, v[j]);
     }
     for (int i = 0;; ++i) {
       if (nb == 0) break;
@@ -481,18 +535,18 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       // batch i+1 and is issued only if that batch's list is out: never block on it here (its
       // publication may itself be waiting for this batch to be consumed).
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        int li = i, ln = nb, lrow = cw * 8 + 4;
+      for (int h = 0; h < RND; ++h) {
+        int li = i, ln = nb, lrow = cw * ROWS + 4 * (h + 1);
         bool ls = skipb;
-        if (h == 1) {
+        if (h == RND - 1) {
           ahead = __all_sync(0xffffffffu,
                              mbar_test_wait(&ctl.list[(i + 1) & 1], ((i + 1) >> 1) & 1));
           if (ahead) header(i + 1, nb2, skip2);
-          li = i + 1; ln = nb2; lrow = cw * 8; ls = skip2;
+          li = i + 1; ln = nb2; lrow = cw * ROWS; ls = skip2;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int row = cw * 8 + 4 * h + j;
+          const int row = cw * ROWS + 4 * h + j;
           if (do_store && row < nbr) store_row(bhi, blo, row, v[j]);
           load_row(li, ln, ls, lrow + j, v[j]);
         }
@@ -504,12 +558,13 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
       if (!ahead) {
         header(i + 1, nb2, skip2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) load_row(i + 1, nb2, skip2, cw * 8 + j, v[j]);
+        for (int j = 0; j < 4; ++j) load_row(i + 1, nb2, skip2, cw * ROWS + j, v[j]);
       }
       nb = nb2;
       skipb = skip2;
     }
-  } else if (warp == 12) {
+    }
+  } else if (MODE != 1 && warp == 12) {
     // ======================= MMA issuer ============================================================
     if (lane == 0) {
       // transposed product: D[channel, pixel] += F^T[channel, g] * W^T[g, pixel].  The feature tile
@@ -533,7 +588,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
         const int votes_now = *reinterpret_cast<volatile int *>(&ctl.skip[st]);
         const int votes = votes_now - seen[st];
         seen[st] = votes_now;
-        if (votes < 4) {
+        if (MODE != 1 && votes < 4) {
           const int nk = (nb + 15) >> 4;
 #pragma unroll 1
           for (int ks = 0; ks < nk; ++ks) {
@@ -597,7 +652,7 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   __syncthreads();
   tc_fence_after();
   if (warp == 0) TC_STAMP(3, 0, 2);
-  if (warp < 12) {
+  if (MODE != 1 && warp < 12) {
     const bool any = ctl.any_mma != 0;
     bool use_bg = false;
 #pragma unroll
@@ -667,7 +722,9 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
   if (warp == 0) TC_STAMP(3, 0, 3);
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc<L::TCOLS>(tb);
+  if constexpr (MODE != 1) {
+    if (warp == 12) tmem_dealloc<L::TCOLS>(tb);
+  }
 }
 
 // epilogue: 1 = TMA tensor stores from a staged box (UTMASTG), 0 = per-lane streaming stores
@@ -704,7 +761,7 @@ bool make_render_map(CUtensorMap *m, float *render, int D, int W, int H) {
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NATOM, bool V3>
+template <int NATOM, bool V3, int MODE = 0>
 int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
               int H, const int *offsets, const int *ids, float *render, float *alphas,
               int *last_ids, unsigned char *wcache, int *wmeta, int *wlist, int *wcount,
@@ -713,14 +770,15 @@ int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, c
   const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
   const int hh = (H + 7) / 8;
   {   // per-device attribute: set on every launch (a process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(blend_fwd_tc<NATOM, V3>,
+    cudaError_t e = cudaFuncSetAttribute(blend_fwd_tc<NATOM, V3, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
   }
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  const int use_tma = (g_fwd_tma_epilogue && make_render_map(&tmap, render, D, W, H)) ? 1 : 0;
-  blend_fwd_tc<NATOM, V3><<<dim3(tw, hh), TC_THREADS, L::BYTES, st>>>(
+  const int use_tma =
+      (MODE != 1 && g_fwd_tma_epilogue && make_render_map(&tmap, render, D, W, H)) ? 1 : 0;
+  blend_fwd_tc<NATOM, V3, MODE><<<dim3(tw, hh), TcCfg<MODE>::THREADS, L::BYTES, st>>>(
       reinterpret_cast<const float4 *>(geom), colors, D, ch0, nch, bg, W, H, tw, offsets, ids,
       render, alphas, last_ids, wcache, wmeta, wlist, wcount, tmap, use_tma);
   return (int)cudaGetLastError();
@@ -768,6 +826,59 @@ int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const f
       }
     }
 #undef GAGS_TC_ARGS
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// ---- the forward in two passes, split at the weight-tile cache -------------------------------------
+// Pass 1 (weights): everything that depends on the geometry only — tile walk, exact cull, alpha,
+// transmittance chain — writes alphas (+ last_ids), the blended batches' weight tiles and id lists.
+// Pass 2 (blend): render = cached weights x features on the tensor cores.  Between the two the
+// caller knows exactly which feature rows the view reads (gags_blend_cache_mark_rows), which is
+// what lets a lazily-updated feature table be brought up to date for those rows only.
+extern "C" int gags_blend_fwd_weights(const float *geom, int32_t width, int32_t height,
+                                      const int32_t *offsets, const int32_t *flatten_ids,
+                                      float *alphas, int32_t *last_ids, void *wcache,
+                                      int32_t *wmeta, int32_t *wlist, int32_t *wcount,
+                                      void *stream) {
+  if (!geom || !offsets || !alphas || !wcache || !wmeta || !wlist || !wcount || width <= 0 ||
+      height <= 0)
+    return GAGS_EINVAL;
+  if (g_gags_blend_impl == 1) return GAGS_EINVAL;
+  if (!gags_aligned16(geom) || !gags_aligned16(wcache)) return GAGS_EALIGN;
+  return launch_tc<1, true, 1>(geom, nullptr, 64, 0, 64, nullptr, width, height, offsets,
+                               flatten_ids, nullptr, alphas, last_ids,
+                               reinterpret_cast<unsigned char *>(wcache), wmeta, wlist, wcount,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int gags_blend_fwd_from_cache(const float *colors, int32_t D, const float *background,
+                                         int32_t width, int32_t height, const int32_t *offsets,
+                                         const void *wcache, const int32_t *wmeta,
+                                         const int32_t *wlist, const int32_t *wcount,
+                                         const float *alphas, float *render, void *stream) {
+  if (!colors || !offsets || !wcache || !wmeta || !wlist || !wcount || !alphas || !render ||
+      width <= 0 || height <= 0)
+    return GAGS_EINVAL;
+  if (D <= 32 || D % 16 != 0 || g_gags_blend_impl == 1) return GAGS_EINVAL;
+  if (!gags_aligned16(colors) || !gags_aligned16(wcache) || !gags_aligned16(render)) return GAGS_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *wc = const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(wcache));
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const int natom = (nch + 63) / 64;
+    int rc;
+#define GAGS_TC2_ARGS nullptr, colors, D, ch0, nch, background, width, height, offsets, nullptr,      \
+                      render, const_cast<float *>(alphas), nullptr, wc, const_cast<int *>(wmeta),   \
+                      const_cast<int *>(wlist), const_cast<int *>(wcount), st
+    switch (natom) {
+      case 1: rc = launch_tc<1, true, 2>(GAGS_TC2_ARGS); break;
+      case 2: rc = launch_tc<2, true, 2>(GAGS_TC2_ARGS); break;
+      case 3: rc = launch_tc<3, true, 2>(GAGS_TC2_ARGS); break;
+      default: rc = launch_tc<4, true, 2>(GAGS_TC2_ARGS); break;
+    }
+#undef GAGS_TC2_ARGS
     if (rc != 0) return rc;
   }
   return 0;

@@ -183,6 +183,21 @@ l1_loss_sam_kernel(const float4 *__restrict__ r, const int *__restrict__ seg3,
   }
 }
 
+// ONE Adam update, spelled with explicit roundings: every kernel below (dense, row-sparse, lazy,
+// peer, multicast, tail) must produce the same bits for the same operands — the row-sparse and lazy
+// forms are specified as "bit-identical to the dense pass" — so nothing is left to the compiler's
+// choice of which product of `b1*m + (1-b1)*g` to contract into an FMA.
+__device__ __forceinline__ void adam_update1(float &p, float g, float &m, float &v, float step_size,
+                                             float b1, float b2, float omb1, float omb2,
+                                             float inv_sqrt_bc2, float eps) {
+  m = fmaf(omb1, g, __fmul_rn(b1, m));
+  v = fmaf(omb2, __fmul_rn(g, g), __fmul_rn(b2, v));
+  const float denom = fmaf(sqrtf(v), inv_sqrt_bc2, eps);
+  p = fmaf(-step_size, __fdiv_rn(m, denom), p);
+}
+#define GAGS_ADAM1(P, G, M, V, c) \
+  adam_update1(P.c, G.c, M.c, V.c, step_size, b1, b2, omb1, omb2, inv_sqrt_bc2, eps);
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
             float4 *__restrict__ v, long long n4, float step_size, float b1, float b2,
@@ -196,10 +211,6 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
     float4 ma = m[i0], va = v[i0], pa = p[i0];
     float4 gb = ga, mb = ma, vb = va, pb = pa;
     if (two) { gb = g[i1]; mb = m[i1]; vb = v[i1]; pb = p[i1]; }
-#define GAGS_ADAM1(P, G, M, V, c)                                 \
-    M.c = b1 * M.c + omb1 * G.c;                                  \
-    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
-    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
     GAGS_ADAM1(pa, ga, ma, va, x) GAGS_ADAM1(pa, ga, ma, va, y)
     GAGS_ADAM1(pa, ga, ma, va, z) GAGS_ADAM1(pa, ga, ma, va, w)
     m[i0] = ma; v[i0] = va; p[i0] = pa;
@@ -210,7 +221,6 @@ adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__
       m[i1] = mb; v[i1] = vb; p[i1] = pb;
       if (zero_grad) g[i1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#undef GAGS_ADAM1
   }
 }
 
@@ -241,10 +251,6 @@ adam_rows_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restr
     float4 ga = zero, gb = zero;
     if (fa) ga = g[i0];
     if (fb) gb = g[i1];
-#define GAGS_ADAM1(P, G, M, V, c)                                 \
-    M.c = b1 * M.c + omb1 * G.c;                                  \
-    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
-    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
     GAGS_ADAM1(pa, ga, ma, va, x) GAGS_ADAM1(pa, ga, ma, va, y)
     GAGS_ADAM1(pa, ga, ma, va, z) GAGS_ADAM1(pa, ga, ma, va, w)
     m[i0] = ma; v[i0] = va; p[i0] = pa;
@@ -255,8 +261,91 @@ adam_rows_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restr
       m[i1] = mb; v[i1] = vb; p[i1] = pb;
       if (fb) g[i1] = zero;
     }
-#undef GAGS_ADAM1
   }
+}
+
+// ---- lazily evaluated Adam for a row-sparse gradient --------------------------------------------
+// With g = 0 a row's Adam step depends on nothing but the row's own (p, m, v) and the step's two
+// scalars, so it does not have to be TAKEN at that step: a row that no view touches for k steps can
+// take those k zero-gradient steps later, in registers, in one visit — the same fp32 operations in
+// the same order, hence bit-identical to the dense pass, for 1/k of its memory traffic.  `last[r]`
+// is the optimiser step row r is current to; `consts[s]` = (lr / (1 - b1^s), 1 / sqrt(1 - b2^s)) as
+// gags_adam_step computes them for step s (written by the host, one entry per step).  One call:
+// every selected row (flags[r] != 0, or all rows when flags == NULL) first takes the zero-gradient
+// steps last[r]+1 .. t_to; then, if t_apply != 0 (= t_to + 1), the step t_apply with its gradient
+// row, which is re-zeroed.  The two-pass forward (gags_blend_fwd_weights -> mark rows -> here with
+// t_apply = 0 -> gags_blend_fwd_from_cache) brings exactly the rows a view reads up to date before
+// they are read; the optimiser step then visits only the rows the view (or, multi-GPU, any rank's
+// view) touched; a flush (flags == NULL) materialises the whole table.
+// A zero-gradient step runs the very same adam_update1 with the gradient operand `gzero` (a kernel
+// ARGUMENT holding 0.f, so that nothing is folded away): e.g. fma(1-b1, +0, -0) is +0, exactly what
+// the dense pass leaves in m.
+struct AdamC { float b1, b2, omb1, omb2, eps; };
+
+__global__ void __launch_bounds__(256)
+adam_lazy_rows_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ m,
+                      float4 *__restrict__ v, const unsigned char *__restrict__ flags,
+                      int *__restrict__ last, const float2 *__restrict__ consts, long long rows,
+                      int row4, int t_to, int t_apply, float gzero, AdamC c) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const float b1 = c.b1, b2 = c.b2, omb1 = c.omb1, omb2 = c.omb2, eps = c.eps;
+#define GAGS_ADAM4(P, G, M, V)                                                        \
+    GAGS_ADAM1(P, G, M, V, x) GAGS_ADAM1(P, G, M, V, y) GAGS_ADAM1(P, G, M, V, z) GAGS_ADAM1(P, G, M, V, w)
+  for (long long base = warp * 32; base < rows; base += nwarps * 32) {
+    const long long r = base + lane;
+    bool f = r < rows && (flags == nullptr || flags[r] != 0);
+    const int s0 = f ? last[r] : 0;
+    if (f && t_apply == 0 && s0 >= t_to) f = false;          // already current
+    unsigned mask = __ballot_sync(0xffffffffu, f);
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const long long row = base + k;
+      const int sk = __shfl_sync(0xffffffffu, s0, k);
+      const long long rb = row * (long long)row4;
+      for (int c0 = 0; c0 < row4; c0 += 64) {
+        const int ca = c0 + lane, cb = c0 + 32 + lane;
+        const bool ha = ca < row4, hb = cb < row4;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pa = zero, ma = zero, va = zero, pb = zero, mb = zero, vb = zero, ga = zero, gb = zero;
+        if (ha) { pa = p[rb + ca]; ma = m[rb + ca]; va = v[rb + ca]; }
+        if (hb) { pb = p[rb + cb]; mb = m[rb + cb]; vb = v[rb + cb]; }
+        if (t_apply != 0) {
+          if (ha) ga = g[rb + ca];
+          if (hb) gb = g[rb + cb];
+        }
+        // a row whose moments are exactly zero does not move under zero-gradient steps
+        const bool still = ma.x == 0.f && ma.y == 0.f && ma.z == 0.f && ma.w == 0.f && va.x == 0.f &&
+                           va.y == 0.f && va.z == 0.f && va.w == 0.f && mb.x == 0.f && mb.y == 0.f &&
+                           mb.z == 0.f && mb.w == 0.f && vb.x == 0.f && vb.y == 0.f && vb.z == 0.f &&
+                           vb.w == 0.f;
+        if (!__all_sync(0xffffffffu, still)) {
+          const float4 gz = make_float4(gzero, gzero, gzero, gzero);
+#pragma unroll 1
+          for (int s = sk + 1; s <= t_to; ++s) {
+            const float2 cs = __ldg(consts + s);
+            const float step_size = cs.x, inv_sqrt_bc2 = cs.y;
+            GAGS_ADAM4(pa, gz, ma, va)
+            GAGS_ADAM4(pb, gz, mb, vb)
+          }
+        }
+        if (t_apply != 0) {
+          const float2 cs = __ldg(consts + t_apply);
+          const float step_size = cs.x, inv_sqrt_bc2 = cs.y;
+          GAGS_ADAM4(pa, ga, ma, va)
+          GAGS_ADAM4(pb, gb, mb, vb)
+          if (ha) g[rb + ca] = zero;
+          if (hb) g[rb + cb] = zero;
+        }
+        if (ha) { p[rb + ca] = pa; m[rb + ca] = ma; v[rb + ca] = va; }
+        if (hb) { p[rb + cb] = pb; m[rb + cb] = mb; v[rb + cb] = vb; }
+      }
+      if (lane == 0) last[row] = t_apply != 0 ? t_apply : t_to;
+    }
+  }
+#undef GAGS_ADAM4
 }
 
 // ---- gradient all-reduce + Adam + parameter all-gather as ONE kernel over NVLink peer memory ---
@@ -292,13 +381,8 @@ adam_peer_kernel(PeerPtrs pp, int world, int rank, float4 *__restrict__ m, float
 #pragma unroll
     for (int q = 0; q < MAXW; ++q)
       if (q < world) { g.x += gq[q].x; g.y += gq[q].y; g.z += gq[q].z; g.w += gq[q].w; }
-#define GAGS_ADAM1(P, G, M, V, c)                                 \
-    M.c = b1 * M.c + omb1 * G.c;                                  \
-    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
-    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
     GAGS_ADAM1(pa, g, ma, va, x) GAGS_ADAM1(pa, g, ma, va, y)
     GAGS_ADAM1(pa, g, ma, va, z) GAGS_ADAM1(pa, g, ma, va, w)
-#undef GAGS_ADAM1
     m[k] = ma;
     v[k] = va;
 #pragma unroll
@@ -336,10 +420,6 @@ adam_multicast_kernel(const float4 *mc_grad, float4 *mc_param, const float4 *__r
       const long long k = k0 + u * stride;
       if (k < count) { pa[u] = p_local[start + k]; ma[u] = m[k]; va[u] = v[k]; }
     }
-#define GAGS_ADAM1(P, G, M, V, c)                                 \
-    M.c = b1 * M.c + omb1 * G.c;                                  \
-    V.c = b2 * V.c + omb2 * (G.c * G.c);                          \
-    P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long k = k0 + u * stride;
@@ -354,7 +434,6 @@ adam_multicast_kernel(const float4 *mc_grad, float4 *mc_param, const float4 *__r
                      : "memory");
       }
     }
-#undef GAGS_ADAM1
   }
 }
 
@@ -472,10 +551,9 @@ __global__ void adam_tail_kernel(float *p, float *g, float *m, float *v, long lo
   const long long i = start + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i];
-  const float mi = b1 * m[i] + omb1 * gi;
-  const float vi = b2 * v[i] + omb2 * (gi * gi);
-  p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
-  m[i] = mi; v[i] = vi;
+  float mi = m[i], vi = v[i], pi = p[i];
+  adam_update1(pi, gi, mi, vi, step_size, b1, b2, omb1, omb2, inv_sqrt_bc2, eps);
+  p[i] = pi; m[i] = mi; v[i] = vi;
   if (zero_grad) g[i] = 0.f;
 }
 
@@ -642,6 +720,56 @@ extern "C" int gags_adam_step_rows(float *param, float *grad, float *exp_avg, fl
   GAGS_CHECK_LAUNCH();
   cudaError_t e = cudaMemsetAsync(row_flags, 0, (size_t)rows, st);
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+// (lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step)) exactly as gags_adam_step forms them: the host
+// writes one pair per optimiser step into the table gags_adam_lazy_rows reads.
+extern "C" int gags_adam_step_consts(double lr, double beta1, double beta2, int32_t step,
+                                     float *out2_host) {
+  if (!out2_host || step < 1) return GAGS_EINVAL;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  out2_host[0] = (float)(lr / bc1);
+  out2_host[1] = (float)(1.0 / sqrt(bc2));
+  return 0;
+}
+
+// Lazily evaluated Adam on the rows selected by row_flags (NULL = every row), see
+// adam_lazy_rows_kernel.  t_apply is 0 (catch up only; grad may be NULL) or t_to + 1.  With
+// clear_flags the flags are zeroed behind the kernel.
+extern "C" int gags_adam_lazy_rows(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                   uint8_t *row_flags, int32_t *last_step, const float *step_consts,
+                                   int64_t rows, int32_t D, int32_t t_to, int32_t t_apply,
+                                   double beta1, double beta2, double eps, int32_t clear_flags,
+                                   void *stream) {
+  if (!param || !exp_avg || !exp_avg_sq || !last_step || !step_consts || rows < 0 || D < 4 ||
+      t_to < 0)
+    return GAGS_EINVAL;
+  if (D % 4 != 0) return GAGS_EINVAL;
+  if (t_apply != 0 && (t_apply != t_to + 1 || !grad)) return GAGS_EINVAL;
+  if (clear_flags && !row_flags) return GAGS_EINVAL;
+  if (!gags_aligned16(param) || !gags_aligned16(exp_avg) || !gags_aligned16(exp_avg_sq) ||
+      (grad && !gags_aligned16(grad)) || ((uintptr_t)step_consts & 7))
+    return GAGS_EALIGN;
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamC c;
+  c.b1 = (float)beta1; c.b2 = (float)beta2;
+  c.omb1 = (float)(1.0 - beta1); c.omb2 = (float)(1.0 - beta2);
+  c.eps = (float)eps;
+  long long blocks = (rows + 255) / 256;                       // one row per lane-slot of flags
+  const long long cap = (long long)gags_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_lazy_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+      reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),
+      reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), row_flags,
+      last_step, reinterpret_cast<const float2 *>(step_consts), rows, D / 4, t_to, t_apply, 0.f, c);
+  GAGS_CHECK_LAUNCH();
+  if (clear_flags) {
+    cudaError_t e = cudaMemsetAsync(row_flags, 0, (size_t)rows, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
 }
 
 // Tuning hook for the two exchange kernels (tools/peer_rate.py sweeps it): CTAs per SM of their

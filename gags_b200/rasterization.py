@@ -37,6 +37,10 @@ direct_grad_accumulation = False
 # chain, see csrc/blend_tc_common.cuh tc3_chain8) and info["last_ids"] is None; set this to keep it.
 want_last_ids = False
 
+# A lazily-updated feature table (optim.LazyRows) is rendered in two passes (see lazy_owners);
+# False forces the flush + single-pass route (A/B switch for tests and bench).
+two_pass_forward = True
+
 # Keep the forward's blend-weight tiles for the feature backward (training with frozen geometry).
 # The parity tests switch it off to exercise the recomputing backward kernels as well.
 weight_cache = True
@@ -493,6 +497,13 @@ class RowFlags:
 row_flags: Dict[int, RowFlags] = {}
 
 
+# data_ptr of a feature table -> optim.LazyRows: the table is updated lazily (rows no view touched
+# are behind by some optimiser steps).  A forward that keeps its weight tiles runs in two passes —
+# weights pass, flag + catch up exactly the rows it blends, blend pass; any other forward flushes the
+# whole table first.
+lazy_owners: Dict = {}
+
+
 def _direct(colors) -> bool:
     """Reduce this tensor's feature gradient straight into its `.grad`?  Process-wide switch or the
     per-parameter opt-in an optimiser sets on the parameters it keeps a persistent gradient for."""
@@ -613,7 +624,8 @@ def fused_l1_backward(render_dhw, seg_hw, emb, mask_hw=None):
         _C.ptr(cache[3]), _C.ptr(r), _C.ptr(sg), _C.ptr(em), _C.ptr(m), em.shape[0], 1.0 / numel,
         _C.ptr(loss), _C.ptr(v_colors), _C.stream_ptr()), "gags_blend_bwd_features_cached_l1")
     _C.count_launch((D + 255) // 256)
-    _mark_rows(v_colors, cache, h.offsets, width, height)
+    if not ctx.rows_marked:
+        _mark_rows(v_colors, cache, h.offsets, width, height)
     _mark("blend_bwd")
     _finish_fused_backward(render_dhw, h, v_colors, sink)
     return loss[0] / numel
@@ -657,7 +669,8 @@ def fused_sam_backward(render_dhw, seg3, emb, scale_map, want_scale_grad: bool =
         _C.ptr(loss), _C.ptr(v_scale), _C.ptr(v_colors), _C.stream_ptr()),
         "gags_blend_bwd_features_cached_sam")
     _C.count_launch((D + 255) // 256)
-    _mark_rows(v_colors, cache, h.offsets, width, height)
+    if not ctx.rows_marked:
+        _mark_rows(v_colors, cache, h.offsets, width, height)
     _mark("blend_bwd")
     _finish_fused_backward(render_dhw, h, v_colors, sink)
     return loss[0] / numel, v_scale
@@ -669,19 +682,20 @@ class _Blend(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opac, colors, background, geom, offsets, flatten_ids,
-                width, height):
+                width, height, grad_mode=True):
+        # `grad_mode`: torch.is_grad_enabled() at the call site (always off in here, and
+        # needs_input_grad ignores it): a render under no_grad keeps no weight tiles
         _C.require_cuda(colors, geom)
         ctx.sink = None
+        ctx.rows_marked = False
         if (_direct(colors) and colors.is_leaf and colors.requires_grad
                 and colors.dtype == torch.float32 and colors.is_contiguous()):
             ctx.sink = colors
         colors = _f32c(colors)
         N, D = colors.shape
         dev = colors.device
-        if param_ready_events:
-            ev = param_ready_events.pop(colors.data_ptr(), None)
-            if ev is not None:
-                torch.cuda.current_stream(dev).wait_event(ev)
+        ev_param = param_ready_events.pop(colors.data_ptr(), None) if param_ready_events else None
+        lazy = lazy_owners.get(colors.data_ptr()) if lazy_owners else None
         if D > 32 and D % 4 != 0:
             raise ValueError("wide blend needs D % 4 == 0 (rasterization() pads for you)")
         bg = _f32c(background) if background is not None else None
@@ -694,18 +708,60 @@ class _Blend(torch.autograd.Function):
         if need_geo or want_last_ids or not _C.lib.gags_blend_last_ids_optional(D):
             last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
         cache = None
-        if (weight_cache and ctx.needs_input_grad[3] and not need_geo
+        if (weight_cache and grad_mode and ctx.needs_input_grad[3] and not need_geo
                 and _C.lib.gags_blend_cache_supported(D)):
             n_tiles = offsets.numel() - 1
             slots = int(_C.lib.gags_blend_cache_slots(flatten_ids.numel(), n_tiles))
             lease = _CacheLease(dev, slots, ((width + TILE - 1) // TILE) * ((height + 7) // 8))
             cache = lease.bufs
-            _C.check(_C.lib.gags_blend_fwd_cached(
-                _C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height, _C.ptr(offsets),
-                _C.ptr(flatten_ids), _C.ptr(render), _C.ptr(alphas), _C.ptr(last_ids),
-                _C.ptr(cache[0]), _C.ptr(cache[1]), _C.ptr(cache[2]), _C.ptr(cache[3]),
-                _C.stream_ptr()), "gags_blend_fwd_cached")
+            cur = torch.cuda.current_stream(dev)
+            # the gradient buffer's row flags (persistent .grad of a row-sparse optimiser), if any
+            rf = None
+            if ctx.sink is not None and ctx.sink.grad is not None and row_flags:
+                rf = row_flags.get(ctx.sink.grad.data_ptr())
+            if lazy is not None and rf is not None and lazy.flags is rf and two_pass_forward:
+                # two passes: nothing before the catch-up reads a feature, so exactly the rows this
+                # view blends are brought up to date — and the weights pass does not have to wait
+                # for the previous optimiser step / exchange either
+                _C.check(_C.lib.gags_blend_fwd_weights(
+                    _C.ptr(geom), width, height, _C.ptr(offsets), _C.ptr(flatten_ids),
+                    _C.ptr(alphas), _C.ptr(last_ids), _C.ptr(cache[0]), _C.ptr(cache[1]),
+                    _C.ptr(cache[2]), _C.ptr(cache[3]), _C.stream_ptr()), "gags_blend_fwd_weights")
+                _mark("fwd_weights")
+                if ev_param is not None:
+                    cur.wait_event(ev_param)
+                    ev_param = None
+                evs = sink_ready_events.pop(ctx.sink.grad.data_ptr(), None)
+                if evs is not None:                  # flags / gradient still in use by the last step
+                    cur.wait_event(evs)
+                _C.check(_C.lib.gags_blend_cache_mark_rows(
+                    width, height, _C.ptr(offsets), _C.ptr(cache[1]), _C.ptr(cache[2]),
+                    _C.ptr(cache[3]), _C.ptr(rf.flags), _C.stream_ptr()), "gags_blend_cache_mark_rows")
+                rf.dirty = True
+                ctx.rows_marked = True
+                lazy.catch_up(rf.flags)
+                _mark("rows_catch_up")
+                _C.check(_C.lib.gags_blend_fwd_from_cache(
+                    _C.ptr(colors), D, _C.ptr(bg), width, height, _C.ptr(offsets), _C.ptr(cache[0]),
+                    _C.ptr(cache[1]), _C.ptr(cache[2]), _C.ptr(cache[3]), _C.ptr(alphas),
+                    _C.ptr(render), _C.stream_ptr()), "gags_blend_fwd_from_cache")
+                _C.count_launch(2)
+            else:
+                if ev_param is not None:
+                    cur.wait_event(ev_param)
+                    ev_param = None
+                if lazy is not None:
+                    lazy.flush()
+                _C.check(_C.lib.gags_blend_fwd_cached(
+                    _C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width, height, _C.ptr(offsets),
+                    _C.ptr(flatten_ids), _C.ptr(render), _C.ptr(alphas), _C.ptr(last_ids),
+                    _C.ptr(cache[0]), _C.ptr(cache[1]), _C.ptr(cache[2]), _C.ptr(cache[3]),
+                    _C.stream_ptr()), "gags_blend_fwd_cached")
         else:
+            if ev_param is not None:
+                torch.cuda.current_stream(dev).wait_event(ev_param)
+            if lazy is not None:
+                lazy.flush()
             _C.check(_C.lib.gags_blend_fwd(_C.ptr(geom), _C.ptr(colors), D, _C.ptr(bg), width,
                                            height, _C.ptr(offsets), _C.ptr(flatten_ids),
                                            _C.ptr(render), _C.ptr(alphas), _C.ptr(last_ids),
@@ -768,7 +824,7 @@ class _Blend(torch.autograd.Function):
                                                 _C.ptr(va), _C.ptr(v_m), _C.ptr(v_c), _C.ptr(v_o),
                                                 _C.ptr(v_colors), st), "gags_blend_bwd_full")
             _C.count_launch(2)
-        if need_col:
+        if need_col and not ctx.rows_marked:
             _mark_rows(v_colors, cache if not need_geo else None, offsets, width, height)
         _mark("blend_bwd")
         if ctx.needs_input_grad[4] and bg is not None:
@@ -777,7 +833,7 @@ class _Blend(torch.autograd.Function):
             if sink.grad is None:
                 sink.grad = v_colors                 # first view of the step: adopt the buffer
             v_colors = None                          # already accumulated; nothing for autograd to add
-        return v_m, v_c, v_o, v_colors, v_bg, None, None, None, None, None
+        return v_m, v_c, v_o, v_colors, v_bg, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -862,7 +918,8 @@ def rasterize_view(means, quats, scales, opacities, colors, viewmat, fx, fy, cx,
     # [0] view makes .retain_grad() on it behave as in the reference (:75-78)
     means2d_c = means2d.unsqueeze(0)
     render, alphas, last_ids = _Blend.apply(means2d_c[0], conics, opac, cols, bg, geom,
-                                            binned["offsets"], binned["flatten_ids"], width, height)
+                                            binned["offsets"], binned["flatten_ids"], width, height,
+                                            torch.is_grad_enabled())
     _mark("blend_fwd")
     last_ctx = getattr(_tls, "last_cached_ctx", None)
     if last_ctx is not None:

@@ -52,6 +52,7 @@ class GaussianModel:
 
     # ---- state tuple (scene/gaussian_model.py:63-113) -------------------------------------------
     def capture(self):
+        self._flush_lazy()
         return (self.active_sh_degree, self._xyz, self._features_dc, self._features_rest,
                 self._scaling, self._rotation, self._opacity, self.max_radii2D,
                 self.xyz_gradient_accum, self.denom, self.optimizer.state_dict(),
@@ -133,7 +134,14 @@ class GaussianModel:
             names += [f"semantic_{i}" for i in range(self._semantic_feature.shape[1])]
         return names
 
+    def _flush_lazy(self):
+        """A lazily-updated feature table (FusedAdam(lazy_rows)) is materialised before it is read."""
+        opt = getattr(self, "optimizer", None)
+        if opt is not None and hasattr(opt, "flush"):
+            opt.flush()
+
     def save_ply(self, path):
+        self._flush_lazy()
         """Same file the reference writes: one float32 `vertex` element, SH coefficients stored
         channel-major (the [N,K,3] tensors transposed to [N,3,K] and flattened), raw (pre-activation)
         opacity / scale / rotation, then semantic_{i}."""
@@ -227,8 +235,13 @@ class GaussianModel:
             from ..optim import FusedAdam
             # row-sparse gradient handling (optim.py): on unless GAGS_B200_SPARSE_ADAM=0
             import os
-            self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15,
-                                       sparse_rows=os.environ.get("GAGS_B200_SPARSE_ADAM", "1") != "0")
+            sparse = os.environ.get("GAGS_B200_SPARSE_ADAM", "1") != "0"
+            # ... and lazily evaluated on top of that unless GAGS_B200_LAZY_ADAM=0: between flushes
+            # `_semantic_feature` holds each row as of its last visit; render(), capture() and
+            # save_ply() handle that, other readers call self.optimizer.flush() first
+            lazy = sparse and os.environ.get("GAGS_B200_LAZY_ADAM", "1") != "0"
+            self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15, sparse_rows=sparse,
+                                       lazy_rows=lazy)
         else:
             self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
         self.xyz_scheduler_args = get_expon_lr_func(

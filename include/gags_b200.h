@@ -197,6 +197,21 @@ int gags_blend_fwd_cached(const float *geom, const float *colors, int32_t D,
                           const int32_t *offsets, const int32_t *flatten_ids, float *render,
                           float *alphas, int32_t *last_ids, void *wcache, int32_t *wmeta,
                           int32_t *wlist, int32_t *wcount, void *stream);
+/* The cached forward in two passes, split at the weight-tile cache (same buffers as
+ * gags_blend_fwd_cached; together they produce exactly its outputs):
+ *   gags_blend_fwd_weights    — the geometry-only half (tile walk, cull, alpha, transmittance):
+ *                               alphas, last_ids (may be NULL), weight tiles + batch lists; reads no
+ *                               feature.  After it, gags_blend_cache_mark_rows names the feature rows
+ *                               the view will read.
+ *   gags_blend_fwd_from_cache — render = cached weights x colors (+ (1 - alpha) * background).      */
+int gags_blend_fwd_weights(const float *geom, int32_t width, int32_t height, const int32_t *offsets,
+                           const int32_t *flatten_ids, float *alphas, int32_t *last_ids,
+                           void *wcache, int32_t *wmeta, int32_t *wlist, int32_t *wcount,
+                           void *stream);
+int gags_blend_fwd_from_cache(const float *colors, int32_t D, const float *background, int32_t width,
+                              int32_t height, const int32_t *offsets, const void *wcache,
+                              const int32_t *wmeta, const int32_t *wlist, const int32_t *wcount,
+                              const float *alphas, float *render, void *stream);
 int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
                                    const int32_t *offsets, const void *wcache,
                                    const int32_t *wmeta, const int32_t *wlist,
@@ -295,6 +310,19 @@ int gags_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
 int gags_adam_step_rows(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                         uint8_t *row_flags, int64_t rows, int32_t D, double lr, double beta1,
                         double beta2, double eps, int32_t step, void *stream);
+/* Lazily evaluated form of the same update.  With g = 0 a row's step depends only on the row's own
+ * (p, m, v) and on two scalars of the step, so a row no view touches for k steps takes those k steps
+ * later, in registers, in one visit: the same fp32 operations in the same order (bit-identical to
+ * the dense pass), for 1/k of the memory traffic.  last_step[r] = the optimiser step row r is current
+ * to; step_consts[2 s], [2 s + 1] = the pair gags_adam_step_consts gives for step s (one entry per
+ * step taken, written by the caller).  Every row selected by row_flags (NULL = all rows: a flush)
+ * takes the zero-gradient steps last_step[r]+1 .. t_to, then — if t_apply = t_to + 1 (0 = none) —
+ * step t_apply with its gradient row, which is re-zeroed; last_step[r] is advanced.              */
+int gags_adam_step_consts(double lr, double beta1, double beta2, int32_t step, float *out2_host);
+int gags_adam_lazy_rows(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                        uint8_t *row_flags, int32_t *last_step, const float *step_consts,
+                        int64_t rows, int32_t D, int32_t t_to, int32_t t_apply, double beta1,
+                        double beta2, double eps, int32_t clear_flags, void *stream);
 /* Sets row_flags[g] = 1 for every Gaussian of every batch gags_blend_fwd_cached kept for this view
  * (the rows the cached feature backward reduces into; never clears a flag).                      */
 int gags_blend_cache_mark_rows(int32_t width, int32_t height, const int32_t *offsets,

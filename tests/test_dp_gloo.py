@@ -111,3 +111,19 @@ def test_views_for_rank_one_view_per_rank_is_a_partition():
                 assert v == [(step * world + r) % n_views]
                 seen += v
         assert sorted(seen) == list(range(n_views))
+
+
+def test_row_word_ranges_partition_the_flag_words():
+    """ownership split of parallel.SparsePeerAdam / gags_grad_allreduce_rows: contiguous word ranges
+    that cover [0, ceil(rows / 4)) exactly once (the C side computes the same split)."""
+    from gags_b200.parallel import row_word_ranges
+    for rows in (0, 1, 3, 4, 5, 10007, 2_000_000, 4099):
+        for world in (1, 2, 3, 4, 8, 16):
+            words, rng = row_word_ranges(rows, world)
+            assert words == (rows + 3) // 4 and len(rng) == world
+            assert rng[0][0] == 0 and rng[-1][1] == words
+            for (a0, a1), (b0, b1) in zip(rng[:-1], rng[1:]):
+                assert a0 <= a1 == b0 <= b1
+    import pytest
+    with pytest.raises(ValueError):
+        row_word_ranges(4, 0)

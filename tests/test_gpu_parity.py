@@ -873,10 +873,20 @@ def test_sparse_rows_training_equals_dense_adam(D, autograd_loss):
         assert max(fracs) < 1.0                                   # the cached route flags a subset
     else:
         assert min(fracs) == 1.0
-    # a gradient that arrives through autograd's own accumulation flags every row
+    # a gradient that arrives through autograd's own accumulation (no flags) is seen through the
+    # buffer's version counter: the step treats every row as touched
     (p * 2.0).sum().backward()
-    assert int(opt._rows[id(p)][1].flags.sum()) == p.shape[0]
+    st = opt.state[p]
+    rp, rg, rm, rv = p.detach().clone(), p.grad.clone(), st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+    assert float(rg.min()) == 2.0
+    opt.step()
+    _C.check(_C.lib.gags_adam_step(rp.data_ptr(), rg.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                   rp.numel(), 1e-2, 0.9, 0.999, 1e-15, 6, 0, _C.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(p.detach(), rp) and torch.equal(st["exp_avg"], rm)
+    assert float(p.grad.abs().max()) == 0.0
     # a backward that is never applied is dropped by zero_grad
+    (p * 2.0).sum().backward()
     opt.zero_grad(set_to_none=True)
     assert float(p.grad.abs().max()) == 0.0 and int(opt._rows[id(p)][1].flags.sum()) == 0
     # .grad replaced from outside: adopted again at the next step
@@ -886,3 +896,168 @@ def test_sparse_rows_training_equals_dense_adam(D, autograd_loss):
     opt.step()
     assert opt._rows[id(p)][0].data_ptr() == p.grad.data_ptr() and float(p.grad.abs().max()) == 0.0
     assert not R.direct_grad_accumulation
+
+
+# ---------------------------------------------------------------------------------------------
+# lazily evaluated row-sparse Adam (optim.LazyRows, csrc/train_ops.cu adam_lazy_rows_kernel) and
+# the two-pass forward that goes with it
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,D", [(3000, 256), (501, 12), (257, 512), (40, 64)])
+def test_lazy_adam_is_bit_identical_to_dense_steps(rows, D):
+    """14 optimiser steps with a different random ~15 % of the rows carrying a gradient each step:
+    LazyRows (catch up + apply on flagged rows only, rows visited k steps late take their k
+    zero-gradient steps in one go) ends, after flush(), with the bits the dense kernel leaves when it
+    takes every step on every row.  Intermediate catch_up() calls on random subsets (what the
+    two-pass forward does) must not change the outcome; a varying lr is honoured per step."""
+    from gags_b200 import _C
+    from gags_b200.optim import LazyRows
+    g = torch.Generator().manual_seed(3 * rows + D)
+    p0 = torch.randn(rows, D, generator=g).cuda()
+    pd, md, vd = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pl, ml, vl = torch.nn.Parameter(p0.clone()), torch.zeros_like(p0), torch.zeros_like(p0)
+    lz = LazyRows(pl, ml, vl, (0.9, 0.999), 1e-15)
+    grad_l = torch.zeros_like(p0)
+    try:
+        for t in range(1, 15):
+            lr = 1e-2 / t
+            never = torch.arange(rows) % 7 == 3                        # some rows never get a gradient
+            touched = (torch.rand(rows, generator=g) < 0.15) & ~never
+            gr = (torch.randn(rows, D, generator=g) * touched[:, None].float()).cuda()
+            _C.check(_C.lib.gags_adam_step(pd.data_ptr(), gr.clone().data_ptr(), md.data_ptr(),
+                                           vd.data_ptr(), rows * D, lr, 0.9, 0.999, 1e-15, t, 0,
+                                           _C.stream_ptr()))
+            if t % 3 == 0:                                             # a view is about to read these
+                sub = (torch.rand(rows, generator=g) < 0.3).to(torch.uint8).cuda()
+                lz.catch_up(sub)
+                want = sub.bool()
+                assert bool((lz.last[want] == t - 1).all())
+            grad_l.add_(gr)
+            flags = touched.to(torch.uint8).cuda()
+            lz.apply(grad_l, flags, t, lr)
+            torch.cuda.synchronize()
+            assert float(grad_l.abs().max()) == 0.0 and int(flags.sum()) == 0
+            assert bool((lz.last[touched.cuda()] == t).all())
+        assert not torch.equal(pl.detach(), pd)                         # rows really are behind
+        lz.flush()
+        torch.cuda.synchronize()
+        assert bool((lz.last == 14).all())
+        assert torch.equal(pl.detach(), pd) and torch.equal(ml, md) and torch.equal(vl, vd)
+    finally:
+        lz.release()
+
+
+@pytest.mark.parametrize("D,views_per_step", [(64, 1), (256, 1), (128, 2)])
+def test_lazy_training_renders_and_updates_like_dense_training(D, views_per_step):
+    """FusedAdam(lazy_rows=True) through render() + fused loss/backward for 6 optimiser steps against
+    a shadow model that takes the dense Adam step on the same gradients: every render of the lazy
+    model equals the shadow's bit for bit (the two-pass forward caught up exactly the rows it read),
+    rows the views did not touch stay behind in between, and after flush() parameters and moments
+    are bit-identical.  An evaluation render under no_grad flushes by itself."""
+    from gags_b200 import _C, rasterization as R
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.optim import FusedAdam
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_backward_fused
+    dev = torch.device("cuda:0")
+    H, W = 72, 112
+    scene = make_scene(6000, H, W, D, seed=33, n_views=8, sigma_px_median=1.5)
+    g = torch.Generator().manual_seed(6)
+    seg = torch.randint(0, 9, (H, W), generator=g, dtype=torch.int32).to(dev)
+    emb = (0.2 * torch.randn(9, D, generator=g)).to(dev)
+    bg = torch.zeros(3, device=dev)
+
+    def model():
+        pc = GaussianModel(3, device=dev)
+        pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                               scene.features_dc, scene.features_rest, scene.semantic_feature)
+        pc.training_setup(OptimizationParams(), fused_optimizer=True)
+        return pc
+    pc, shadow = model(), model()
+    p = pc._semantic_feature
+    opt = pc.optimizer = FusedAdam([{"params": [p], "lr": 1e-2}], lr=1e-2, eps=1e-15,
+                                   lazy_rows=True)
+    ps = shadow._semantic_feature
+    ms, vs = torch.zeros_like(ps), torch.zeros_like(ps)
+    behind_seen = False
+    view = 0
+    for it in range(1, 7):
+        for _ in range(views_per_step):
+            cam = scene.cameras[view % 8].to(dev)
+            view += 1
+            pkg = render(cam, pc, None, bg)
+            with torch.no_grad():
+                ref = render(cam, shadow, None, bg)["render"]
+            assert torch.equal(pkg["render"].detach(), ref), f"step {it}"
+            l1_backward_fused(pkg["render"], seg, emb)
+        gcopy = p.grad.clone()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        _C.check(_C.lib.gags_adam_step(ps.data_ptr(), gcopy.data_ptr(), ms.data_ptr(), vs.data_ptr(),
+                                       ps.numel(), 1e-2, 0.9, 0.999, 1e-15, it, 0, _C.stream_ptr()))
+        torch.cuda.synchronize()
+        lz = opt._lazy.get(id(p))
+        if lz is not None and lz.behind:
+            behind_seen = behind_seen or not torch.equal(p.detach(), ps.detach())
+            assert int((lz.last < it).sum()) > 0
+    assert behind_seen                                     # the lazy route was really taken
+    # an evaluation render flushes by itself and sees the dense parameters
+    with torch.no_grad():
+        cam = scene.cameras[5].to(dev)
+        a = render(cam, pc, None, bg)["render"]
+        b = render(cam, shadow, None, bg)["render"]
+    assert torch.equal(a, b)
+    st = opt.state[p]
+    assert torch.equal(p.detach(), ps.detach())
+    assert torch.equal(st["exp_avg"], ms) and torch.equal(st["exp_avg_sq"], vs)
+    sd = opt.state_dict()                                  # flushes; layout as torch.optim.Adam
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert not R.direct_grad_accumulation
+
+
+def test_two_pass_forward_equals_single_pass():
+    """gags_blend_fwd_weights + gags_blend_fwd_from_cache == gags_blend_fwd_cached, bit for bit:
+    render, alphas, batch counts and ids (D = 64, 256 and two channel blocks, ragged image, with
+    a background)."""
+    from gags_b200 import _C, rasterization as R
+    # with a background the blend pass forms the final transmittance as 1 - alpha, which is the
+    # single pass's own value only on the chain without last_ids (the training / inference form)
+    for D, (W, H), with_bg in ((64, (96, 64), True), (256, (75, 131), False), (320, (50, 37), True)):
+        sc = front_scene(1500, W, H, D, seed=77 + D)
+        st = _stages(sc)
+        cols = sc["colors"].cuda()
+        bgc = torch.rand(D).cuda() if with_bg else None
+        tw = (W + 15) // 16
+        n_half = tw * ((H + 7) // 8)
+        slots = int(_C.lib.gags_blend_cache_slots(st["flatten_ids"].numel(), tw * ((H + 15) // 16)))
+
+        def bufs():
+            return (torch.zeros(slots * 16384, dtype=torch.uint8, device="cuda"),
+                    torch.zeros(slots * 32, dtype=torch.int32, device="cuda"),
+                    torch.zeros(slots, dtype=torch.int32, device="cuda"),
+                    torch.zeros(n_half + 1, dtype=torch.int32, device="cuda"))
+        c0, c1 = bufs(), bufs()
+        r0, a0 = torch.empty(H, W, D, device="cuda"), torch.empty(H, W, device="cuda")
+        r1, a1 = torch.empty(H, W, D, device="cuda"), torch.empty(H, W, device="cuda")
+        l0 = None if with_bg else torch.empty(H, W, dtype=torch.int32, device="cuda")
+        l1 = None if with_bg else torch.empty(H, W, dtype=torch.int32, device="cuda")
+        s = _C.stream_ptr()
+        _C.check(_C.lib.gags_blend_fwd_cached(_C.ptr(st["geom"]), _C.ptr(cols), D, _C.ptr(bgc), W, H,
+                                              _C.ptr(st["offsets"]), _C.ptr(st["flatten_ids"]),
+                                              _C.ptr(r0), _C.ptr(a0), _C.ptr(l0),
+                                              *[_C.ptr(x) for x in c0], s))
+        _C.check(_C.lib.gags_blend_fwd_weights(_C.ptr(st["geom"]), W, H, _C.ptr(st["offsets"]),
+                                               _C.ptr(st["flatten_ids"]), _C.ptr(a1), _C.ptr(l1),
+                                               *[_C.ptr(x) for x in c1], s))
+        _C.check(_C.lib.gags_blend_fwd_from_cache(_C.ptr(cols), D, _C.ptr(bgc), W, H,
+                                                  _C.ptr(st["offsets"]), *[_C.ptr(x) for x in c1],
+                                                  _C.ptr(a1), _C.ptr(r1), s))
+        torch.cuda.synchronize()
+        assert torch.equal(a0, a1) and (with_bg or torch.equal(l0, l1))
+        assert torch.equal(c0[3][:n_half], c1[3][:n_half]) and int(c1[3][:n_half].sum()) > 0
+        assert torch.equal(r0, r1)
+    assert _C.lib.gags_blend_fwd_weights(None, 4, 4, None, None, None, None, None, None, None, None,
+                                         _C.stream_ptr()) != 0
+    assert _C.lib.gags_blend_fwd_from_cache(None, 64, None, 4, 4, None, None, None, None, None, None,
+                                            None, _C.stream_ptr()) != 0
