@@ -774,6 +774,8 @@ def exchange_check(env):
 
     if peer is not None:
         peer.synchronize()
+        if hasattr(peer, "flush"):
+            peer.flush()
     torch.cuda.synchronize(dev)
     dist.barrier()
     saved_direct = R.direct_grad_accumulation
@@ -817,6 +819,8 @@ def exchange_check(env):
     if peer is not None:
         peer.step()
         peer.synchronize()
+        if hasattr(peer, "flush"):
+            peer.flush()                   # lazily-updated table: materialise before comparing
     else:
         parallel.allreduce_and_step(pc.optimizer, p, world)
         pc.optimizer.zero_grad(set_to_none=True)

@@ -196,15 +196,25 @@ blend_fwd_tc(const float4 *__restrict__ geom, const float *__restrict__ colors, 
     // ======================= blend pass: cached-tile producer (warp 4) =============================
     if (warp == 4) {
       const int nbat = wcount[blockIdx.y * gridDim.x + blockIdx.x];
+      // The batch metadata (list entry -> slot -> 32 Gaussian ids: two dependent global loads) is
+      // fetched one batch AHEAD, before waiting for the stage: it is off the per-batch critical path.
+      int wl = (lane < nbat) ? __ldg(wlist + hbase + lane) : 0;      // list entries of batches 0..31
+      size_t slot_n = 0;
+      int gid_n = -1;
+      if (nbat > 0) {
+        slot_n = (size_t)hbase + (size_t)__shfl_sync(0xffffffffu, wl, 0);
+        gid_n = __ldg(wmeta + slot_n * KB + lane);
+      }
       for (int i = 0; i <= nbat; ++i) {
         const int st = i & 1;
-        if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
-        int gid = -1;
-        size_t slot = 0;
-        if (i < nbat) {
-          slot = (size_t)hbase + (size_t)__ldg(wlist + hbase + i);
-          gid = __ldg(wmeta + slot * KB + lane);
+        const size_t slot = slot_n;
+        const int gid = (i < nbat) ? gid_n : -1;
+        if (i + 1 < nbat) {
+          if (((i + 1) & 31) == 0) wl = (i + 1 + lane < nbat) ? __ldg(wlist + hbase + i + 1 + lane) : 0;
+          slot_n = (size_t)hbase + (size_t)__shfl_sync(0xffffffffu, wl, (i + 1) & 31);
+          gid_n = __ldg(wmeta + slot_n * KB + lane);
         }
+        if (i >= 2) mbar_wait_bounded(&ctl.free_[st], ((i >> 1) - 1) & 1);
         ctl.gid[st][lane] = gid;
         const int nb = __popc(__ballot_sync(0xffffffffu, gid >= 0));
         if (lane == 0) ctl.gcount[st] = nb;

@@ -493,50 +493,61 @@ grad_rows_allreduce_kernel(RowPeerPtrs pp, int world, float4 *mc_grad, const uns
   };
   // (1) this rank's copy of the union flags of ALL rows
   for (long long w = gtid; w < words; w += gthreads) uflags[w] = union_word(w);
-  // (2) the owned words: one warp per word (4 rows), lanes across the row
+  // (2) the owned words: a warp takes 32 consecutive words with one coalesced flag load (the flag
+  // round trip through the fabric is paid once per 128 rows, not once per word), then visits the
+  // flagged words; the flagged rows of a word are summed together, lanes across the row, up to
+  // eight 16-byte reductions in flight per lane
   const long long gwarp = gtid >> 5, nwarps = gthreads >> 5;
-  for (long long w = w0 + gwarp; w < w1; w += nwarps) {
-    unsigned u = 0;
-    if (lane == 0) u = union_word(w);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u == 0u) continue;
+  for (long long wb = w0 + gwarp * 32; wb < w1; wb += nwarps * 32) {
+    const long long wl = wb + lane;
+    const unsigned u = wl < w1 ? union_word(wl) : 0u;
+    unsigned wm = __ballot_sync(0xffffffffu, u != 0u);
+    while (wm) {
+      const int k = __ffs(wm) - 1;
+      wm &= wm - 1;
+      const unsigned uk = __shfl_sync(0xffffffffu, u, k);
+      const long long row0 = (wb + k) * 4;
+      for (int c0 = 0; c0 < row4; c0 += 64) {
+        float4 acc[4][2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (((u >> (8 * r)) & 0xffu) == 0u) continue;                // warp-uniform
-      const long long base = (w * 4 + r) * (long long)row4;
-      for (int c0 = 0; c0 < row4; c0 += 128) {
-        // up to four 16-byte reductions in flight per lane
-        float4 acc[4];
+        for (int r = 0; r < 4; ++r) {
+          if (((uk >> (8 * r)) & 0xffu) == 0u) continue;            // warp-uniform
+          const long long base = (row0 + r) * (long long)row4;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c0 + k * 32 + lane;
-          if (c < row4) {
-            if (MC) {
-              acc[k] = ld_sum_mc(mc_grad + base + c);
-            } else {
-              float4 gq[MAXW];
+          for (int h = 0; h < 2; ++h) {
+            const int c = c0 + h * 32 + lane;
+            if (c < row4) {
+              if (MC) {
+                acc[r][h] = ld_sum_mc(mc_grad + base + c);
+              } else {
+                float4 gq[MAXW];
 #pragma unroll
-              for (int q = 0; q < MAXW; ++q)
-                if (q < world) gq[q] = pp.grad[q][base + c];
-              acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < MAXW; ++q)
+                  if (q < world) gq[q] = pp.grad[q][base + c];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int q = 0; q < MAXW; ++q)
-                if (q < world) {
-                  acc[k].x += gq[q].x; acc[k].y += gq[q].y; acc[k].z += gq[q].z; acc[k].w += gq[q].w;
-                }
+                for (int q = 0; q < MAXW; ++q)
+                  if (q < world) { a.x += gq[q].x; a.y += gq[q].y; a.z += gq[q].z; a.w += gq[q].w; }
+                acc[r][h] = a;
+              }
             }
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c0 + k * 32 + lane;
-          if (c < row4) {
-            if (MC) {
-              st_mc(mc_grad + base + c, acc[k]);
-            } else {
+        for (int r = 0; r < 4; ++r) {
+          if (((uk >> (8 * r)) & 0xffu) == 0u) continue;
+          const long long base = (row0 + r) * (long long)row4;
 #pragma unroll
-              for (int q = 0; q < MAXW; ++q)
-                if (q < world) pp.grad[q][base + c] = acc[k];
+          for (int h = 0; h < 2; ++h) {
+            const int c = c0 + h * 32 + lane;
+            if (c < row4) {
+              if (MC) {
+                st_mc(mc_grad + base + c, acc[r][h]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < MAXW; ++q)
+                  if (q < world) pp.grad[q][base + c] = acc[r][h];
+              }
             }
           }
         }
@@ -908,9 +919,10 @@ extern "C" int gags_grad_allreduce_rows(int32_t world, int32_t rank, const uint6
   long long w0 = per * rank, w1 = per * (rank + 1);
   if (w0 > words) w0 = words;
   if (w1 > words) w1 = words;
-  // a small grid: the exchange is bound by the fabric and runs beside the next view's projection /
-  // tile sort (gags_set_peer_grid overrides, as for the dense exchange kernels)
-  const long long blocks = (long long)gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 2);
+  // latency bound (a flag round trip, then one round trip per flagged word, per warp): many warps,
+  // each with little to do — the kernel is short, what runs beside it waits at most that long
+  // (gags_set_peer_grid overrides, as for the dense exchange kernels)
+  const long long blocks = (long long)gags_sm_count() * (g_peer_ctas_per_sm > 0 ? g_peer_ctas_per_sm : 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define GAGS_ROWS_AR(MC, MAXW)                                                                     \
   grad_rows_allreduce_kernel<MC, MAXW><<<(unsigned)blocks, 256, 0, st>>>(                           \

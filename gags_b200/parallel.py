@@ -300,16 +300,20 @@ class SparsePeerAdam:
     (gags_adam_step_rows: flagged rows read + re-zeroed, every other row takes the g = 0 update).
     Each rank keeps the FULL optimiser state, so no parameter travels at all: per step and rank the
     fabric moves ~0.35 GB per direction instead of the dense exchange's 2 x 2.25 GB (PeerAdam),
-    which stays available for gradients that are not row sparse.  Same arithmetic as FusedAdam on
+    which stays available for gradients that are not row sparse.  With `lazy` (default) the local
+    pass is the lazily evaluated one (optim.LazyRows): it visits the union rows only, and rows no
+    rank touched take their zero-gradient steps when they are next needed.  Same arithmetic as FusedAdam on
     the summed gradient; replicas stay bit-identical because exactly one rank forms each row's sum
     and all ranks apply the same elementwise update to it."""
 
     def __init__(self, param: torch.Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 group=None):
+                 group=None, lazy=None):
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
         from . import _C
         from . import rasterization as R
+        if lazy is None:
+            lazy = os.environ.get("GAGS_B200_LAZY_ADAM", "1") != "0"
         if not (param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()
                 and param.dim() == 2 and param.shape[1] % 4 == 0):
             raise ValueError("SparsePeerAdam needs a contiguous float32 CUDA [N, D] parameter, D % 4 == 0")
@@ -349,6 +353,13 @@ class SparsePeerAdam:
         self._rf = R.RowFlags(self.flags)
         R.row_flags[self.grad.data_ptr()] = self._rf       # the backward flags the rows it touches
         param._gags_direct_grad = True                     # ... and reduces into `.grad` in place
+        # lazily evaluated update (optim.LazyRows): the local pass visits the union rows only, and
+        # the two-pass forward brings the rows a view reads up to date before reading them
+        self.lz = None
+        if lazy:
+            from .optim import LazyRows
+            self.lz = LazyRows(param, self.exp_avg, self.exp_avg_sq, self.betas, self.eps)
+            self.lz.flags = self._rf
         torch.cuda.synchronize(dev)
         self._hdl.barrier()
 
@@ -388,10 +399,13 @@ class SparsePeerAdam:
             self._hdl.barrier()                           # every replica holds the sums; flags read
             if ev:
                 ev[3].record(xs)
-            C.check(C.lib.gags_adam_step_rows(
-                p.data_ptr(), self.grad.data_ptr(), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
-                C.ptr(self.union_flags), self.rows, self.dim, self.lr, self.betas[0], self.betas[1],
-                self.eps, self.step_count, xs.cuda_stream), "gags_adam_step_rows")
+            if self.lz is not None:
+                self.lz.apply(self.grad, self.union_flags, self.step_count, self.lr)
+            else:
+                C.check(C.lib.gags_adam_step_rows(
+                    p.data_ptr(), self.grad.data_ptr(), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
+                    C.ptr(self.union_flags), self.rows, self.dim, self.lr, self.betas[0],
+                    self.betas[1], self.eps, self.step_count, xs.cuda_stream), "gags_adam_step_rows")
             C.check(C.lib.gags_memset_zero(C.ptr(self._flag_bytes), 4 * self.words, xs.cuda_stream),
                     "gags_memset_zero")
             C.count_launch()
@@ -426,9 +440,17 @@ class SparsePeerAdam:
         self._flag_bytes.zero_()
         self._rf.dirty = False
 
+    @torch.no_grad()
+    def flush(self) -> None:
+        """Lazy mode: bring every row up to the current step (before reading the parameter or the
+        moments outside render())."""
+        self.synchronize()
+        if self.lz is not None:
+            self.lz.flush()
+
     def full_moments(self):
         """(exp_avg, exp_avg_sq) of the whole table, flattened copies (every rank holds them)."""
-        self.synchronize()
+        self.flush()
         return self.exp_avg.detach().clone().view(-1), self.exp_avg_sq.detach().clone().view(-1)
 
     def timing_summary(self, last: int = 10):
@@ -443,5 +465,6 @@ class SparsePeerAdam:
                 "adam_ms": sum(e[3].elapsed_time(e[4]) for e in ev) / n}
 
     def state_dict(self):
+        self.flush()
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
                 "lr": self.lr, "betas": self.betas, "eps": self.eps}

@@ -16,14 +16,15 @@ from gags_b200.optim import FusedAdam               # noqa: E402
 rank, world, local = parallel.init_from_env()
 dev = torch.device("cuda", local)
 ok_all = True
-for N, D, frac in ((10007, 64, 0.1), (4099, 12, 0.5), (3, 256, 1.0)):
+for N, D, frac, lazy in ((10007, 64, 0.1, False), (10007, 64, 0.1, True), (4099, 12, 0.5, True),
+                         (3, 256, 1.0, True)):
     torch.manual_seed(0)
     p0 = torch.randn(N, D, device=dev)
     ref = torch.nn.Parameter(p0.clone())
     opt = FusedAdam([ref], lr=1e-2)
     par = torch.nn.Parameter(p0.clone())
-    peer = parallel.SparsePeerAdam(par, lr=1e-2)
-    for step in range(3):
+    peer = parallel.SparsePeerAdam(par, lr=1e-2, lazy=lazy)
+    for step in range(4):
         g = torch.Generator(device=dev).manual_seed(100 * step + rank + 7 * N)
         touched = torch.rand(N, device=dev, generator=g) < frac
         grad = torch.randn(N, D, device=dev, generator=g) * touched[:, None].float()
@@ -38,6 +39,8 @@ for N, D, frac in ((10007, 64, 0.1), (4099, 12, 0.5), (3, 256, 1.0)):
         peer.flags.copy_(touched.to(torch.uint8))
         peer.step()
         peer.synchronize()
+    behind = lazy and frac < 1.0 and not torch.equal(par.detach(), ref.detach())
+    peer.flush()                                     # lazy: every row up to the current step
     torch.cuda.synchronize()
     scale = ref.detach().abs().max()
     err = float((par.detach() - ref.detach()).abs().max() / scale)
@@ -50,10 +53,13 @@ for N, D, frac in ((10007, 64, 0.1), (4099, 12, 0.5), (3, 256, 1.0)):
     allc = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(allc, chk)
     same = all(int(c) == int(allc[0]) for c in allc)
-    ok = err < 1e-6 and err_m < 1e-6 and err_v < 1e-6 and same and clean
+    ok = err < 1e-6 and err_m < 1e-6 and err_v < 1e-6 and same and clean \
+        and (behind or not lazy or frac >= 1.0)
     ok_all = ok_all and ok
-    print(f"rank {rank}: [{N},{D}] multicast={peer.multicast} rel err p {err:.2e} m {err_m:.2e} v {err_v:.2e}, "
+    print(f"rank {rank}: [{N},{D}] lazy={lazy} multicast={peer.multicast} rel err p {err:.2e} m {err_m:.2e} v {err_v:.2e}, "
           f"replicas identical {same}, buffers clean {clean} -> {'OK' if ok else 'FAIL'}", flush=True)
+    if peer.lz is not None:
+        peer.lz.release()
     del peer
 dist.barrier()
 dist.destroy_process_group()

@@ -38,4 +38,4 @@ def test_sparse_peer_adam_matches_allreduce_plus_fused_adam(nvls):
            os.path.join(ROOT, "tests", "multi_gpu", "sparse_peer_adam_check.py")]
     out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("-> OK") == 6, out.stdout[-2000:]
+    assert out.stdout.count("-> OK") == 8, out.stdout[-2000:]

@@ -78,7 +78,13 @@ def full(src, dst):
     traffic = {}
     for r in rows[2:]:
         name = short(r[hdr.index("Kernel Name")])
-        key = "blend_fwd" if "blend_fwd" in name else ("blend_bwd" if "blend_bwd" in name else None)
+        # blend_fwd_tc<NATOM, V3, MODE>: MODE 1 = weights pass, 2 = blend pass, 0 = single pass
+        key = None
+        if "blend_fwd" in name:
+            mode = name.rstrip("> ").split(",")[-1].strip() if "<" in name else "0"
+            key = {"1": "fwd_weights", "2": "blend_fwd"}.get(mode, "blend_fwd_single")
+        elif "blend_bwd" in name:
+            key = "blend_bwd"
         if key is None:
             continue
         tot = 0.0
