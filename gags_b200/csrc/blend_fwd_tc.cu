@@ -841,6 +841,13 @@ int gags_blend_fwd_tc(const float *geom, const float *colors, int32_t D, const f
   return 0;
 }
 
+extern int g_fwd_blend_persistent;
+int gags_blend_fwd_from_cache_persistent(const float *colors, int32_t D, const float *background,
+                                         int32_t width, int32_t height, const int32_t *offsets,
+                                         const unsigned char *wc, const int32_t *wmeta,
+                                         const int32_t *wlist, int32_t *wcount, const float *alphas,
+                                         float *render, cudaStream_t st);
+
 // ---- the forward in two passes, split at the weight-tile cache -------------------------------------
 // Pass 1 (weights): everything that depends on the geometry only — tile walk, exact cull, alpha,
 // transmittance chain — writes alphas (+ last_ids), the blended batches' weight tiles and id lists.
@@ -875,6 +882,10 @@ extern "C" int gags_blend_fwd_from_cache(const float *colors, int32_t D, const f
   if (!gags_aligned16(colors) || !gags_aligned16(wcache) || !gags_aligned16(render)) return GAGS_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *wc = const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(wcache));
+  if (g_fwd_blend_persistent && (D % 4) == 0 && g_fwd_tma_epilogue)
+    return gags_blend_fwd_from_cache_persistent(colors, D, background, width, height, offsets, wc,
+                                                wmeta, wlist, const_cast<int32_t *>(wcount), alphas,
+                                                render, st);
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
     const int natom = (nch + 63) / 64;
@@ -889,6 +900,382 @@ extern "C" int gags_blend_fwd_from_cache(const float *colors, int32_t D, const f
       default: rc = launch_tc<4, true, 2>(GAGS_TC2_ARGS); break;
     }
 #undef GAGS_TC2_ARGS
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// ---- the blend pass as a persistent kernel ---------------------------------------------------------
+// A half tile has only ~4 blended batches at BASELINE config 3, so a one-CTA-per-half-tile blend pass
+// spends about a third of each CTA's life in its prologue (TMEM allocation, barrier set-up, launch)
+// and in the TMEM -> shared -> TMA-store epilogue that nothing of ITS OWN overlaps.  Here ONE CTA per
+// SM owns the whole TMEM (two 256-column accumulators) and 3 A/B stages and pulls half tiles from a
+// global counter:
+//   warp 0      producer: fetches the tile, reads its batch metadata a batch ahead, publishes the
+//               Gaussian ids of each batch and lands its cached weight tile in the A stage (bulk copy)
+//   warp 1      MMA issuer: accumulator (tile k) & 1; commit -> stage free, last batch -> accfull
+//   warps 2-9   converters: 4 feature rows each per batch (gather, bf16 hi/lo split, swizzled store)
+//   warps 10-17 epilogue: drain accumulator (tile k) & 1 while the MMAs of tile k+1 fill the other —
+//               tcgen05.ld -> (+ T bg) -> staging box -> one TMA tensor store per 32 ch x 32 px item
+// The stage ring and every barrier phase run on GLOBAL counters (batches / tiles seen by this CTA),
+// as in the persistent cached backward.  Bit-identical to the one-CTA-per-half-tile blend pass: the
+// same tiles, the same conversions, the same MMA order per accumulator element.
+namespace {
+
+constexpr int PB_THREADS = 576;
+constexpr int PB_NST = 3;          // A/B stages
+constexpr int PB_TQ = 4;           // tile-info ring
+
+struct PbCtl {
+  uint64_t list[PB_NST], full[PB_NST], free_[PB_NST], accfull[2], accfree[2];
+  uint64_t tq_full[PB_TQ], tq_free[PB_TQ];
+  uint32_t tmem_base;
+  int tq_tile[PB_TQ], tq_nbat[PB_TQ];
+  int gcount[PB_NST];
+  int gid[PB_NST][TC_KB];
+  int bg_nonzero[8];
+  alignas(16) float bgs[256];
+};
+
+template <int NATOM>
+struct PbLayout {
+  static constexpr int BPART = NATOM * 4096;
+  static constexpr int A_OFF = 0;                                   // PB_NST x 16 KB
+  static constexpr int B_OFF = PB_NST * 16384;                      // [stage][part][BPART]
+  static constexpr int BOX_OFF = B_OFF + PB_NST * 2 * BPART;        // 8 epilogue warps x 2 x 4 KB
+  static constexpr int CTL_OFF = BOX_OFF + 8 * 2 * 4096;
+  static constexpr int BYTES = CTL_OFF + (int)sizeof(PbCtl) + 1024;
+  static constexpr int MB = (NATOM + 1) / 2;
+};
+static_assert(PbLayout<4>::BYTES <= 232448, "persistent blend pass must fit one SM");
+
+template <int NATOM>
+__global__ void __launch_bounds__(PB_THREADS, 1)
+blend_fwd_pers(const float *__restrict__ colors, int D, int ch0, int nch,
+               const float *__restrict__ bg, int W, int H, int tile_w, int ntiles,
+               const int *__restrict__ offsets, const float *__restrict__ alphas,
+               const unsigned char *__restrict__ wcache, const int *__restrict__ wmeta,
+               const int *__restrict__ wlist, const int *__restrict__ wcount,
+               int *__restrict__ tilectr, const __grid_constant__ CUtensorMap tmap_render) {
+  using L = PbLayout<NATOM>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char *sA = sm + L::A_OFF;
+  unsigned char *sB = sm + L::B_OFF;
+  PbCtl &ctl = *reinterpret_cast<PbCtl *>(sm + L::CTL_OFF);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int k = 0; k < PB_NST; ++k) {
+      mbar_init(&ctl.list[k], 1);
+      mbar_init(&ctl.full[k], 9);                  // 8 converter warps + the producer's expect_tx
+      mbar_init(&ctl.free_[k], 1);
+    }
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&ctl.accfull[k], 1);
+      mbar_init(&ctl.accfree[k], 8);               // epilogue warps
+    }
+    for (int k = 0; k < PB_TQ; ++k) {
+      mbar_init(&ctl.tq_full[k], 1);
+      mbar_init(&ctl.tq_free[k], 8);               // epilogue warps (the last readers of a tile)
+    }
+    mbar_fence_init();
+  }
+  if (tid < 256) {
+    const float b = (bg != nullptr && tid < nch) ? __ldg(bg + ch0 + tid) : 0.f;
+    ctl.bgs[tid] = b;
+    const bool nzw = __any_sync(0xffffffffu, b != 0.f);
+    if (lane == 0) ctl.bg_nonzero[warp] = nzw ? 1 : 0;
+  }
+  if (warp == 1) tmem_alloc<512>(&ctl.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = ctl.tmem_base;
+
+  // tile k of this CTA, as published by the producer: (linear half-tile index or -1, batch count)
+  auto tile_info = [&](int k, int &j, int &nbat) {
+    const int q = k & (PB_TQ - 1);
+    mbar_wait_bounded(&ctl.tq_full[q], (uint32_t)((k / PB_TQ) & 1));
+    j = *reinterpret_cast<volatile int *>(&ctl.tq_tile[q]);
+    nbat = *reinterpret_cast<volatile int *>(&ctl.tq_nbat[q]);
+  };
+
+  if (warp == 0) {
+    // ======================= producer ==============================================================
+    int gs = 0;
+    for (int k = 0;; ++k) {
+      const int q = k & (PB_TQ - 1);
+      if (k >= PB_TQ) mbar_wait_bounded(&ctl.tq_free[q], (uint32_t)(((k / PB_TQ) - 1) & 1));
+      int j = 0;
+      if (lane == 0) j = atomicAdd(tilectr, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= ntiles) j = -1;
+      int nbat = 0, hbase = 0;
+      if (j >= 0) {
+        const int by = j / tile_w, bx = j - by * tile_w;
+        const int tile = (by >> 1) * tile_w + bx;
+        const int s = __ldg(offsets + tile), e = __ldg(offsets + tile + 1);
+        const int cbase = (s >> 5) + tile;
+        hbase = 2 * cbase + (by & 1) * ((e >> 5) + tile + 1 - cbase);
+        nbat = __ldg(wcount + j);
+      }
+      if (lane == 0) {
+        ctl.tq_tile[q] = j;
+        ctl.tq_nbat[q] = nbat;
+        __threadfence_block();
+        mbar_arrive(&ctl.tq_full[q]);
+      }
+      if (j < 0) break;
+      int wl = (lane < nbat) ? __ldg(wlist + hbase + lane) : 0;
+      size_t slot_n = 0;
+      int gid_n = -1;
+      if (nbat > 0) {
+        slot_n = (size_t)hbase + (size_t)__shfl_sync(0xffffffffu, wl, 0);
+        gid_n = __ldg(wmeta + slot_n * TC_KB + lane);
+      }
+      for (int i = 0; i < nbat; ++i, ++gs) {
+        const int st = gs % PB_NST;
+        const size_t slot = slot_n;
+        const int gid = gid_n;
+        if (i + 1 < nbat) {
+          if (((i + 1) & 31) == 0) wl = (i + 1 + lane < nbat) ? __ldg(wlist + hbase + i + 1 + lane) : 0;
+          slot_n = (size_t)hbase + (size_t)__shfl_sync(0xffffffffu, wl, (i + 1) & 31);
+          gid_n = __ldg(wmeta + slot_n * TC_KB + lane);
+        }
+        if (gs >= PB_NST) mbar_wait_bounded(&ctl.free_[st], (uint32_t)(((gs / PB_NST) - 1) & 1));
+        ctl.gid[st][lane] = gid;
+        const int nb = __popc(__ballot_sync(0xffffffffu, gid >= 0));
+        if (lane == 0) ctl.gcount[st] = nb;
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          mbar_arrive(&ctl.list[st]);
+          mbar_expect_tx(&ctl.full[st], 16384u);
+          bulk_g2s(sA + st * 16384, wcache + slot * 16384, 16384u, &ctl.full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer ============================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, true, false);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t f_desc0 = umma_desc_sw128(smem_u32(sB), 4096, 1024);
+      int gs = 0;
+      for (int k = 0;; ++k) {
+        int j, nbat;
+        tile_info(k, j, nbat);
+        if (j < 0) break;
+        const int buf = k & 1;
+        if (k >= 2) mbar_wait_bounded(&ctl.accfree[buf], (uint32_t)(((k >> 1) - 1) & 1));
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int i = 0; i < nbat; ++i, ++gs) {
+          const int st = gs % PB_NST;
+          mbar_wait_bounded(&ctl.list[st], (uint32_t)((gs / PB_NST) & 1));
+          const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+          mbar_wait_bounded(&ctl.full[st], (uint32_t)((gs / PB_NST) & 1));
+          tc_fence_after();
+          const int nk = (nb + 15) >> 4;
+#pragma unroll 1
+          for (int ks = 0; ks < nk; ++ks) {
+            const uint64_t whi = w_desc0 + (uint64_t)((st * 16384 + ks * 32) >> 4);
+            const uint64_t wlo = whi + (uint64_t)(64 >> 4);
+#pragma unroll
+            for (int mb = 0; mb < L::MB; ++mb) {
+              const uint64_t fhi =
+                  f_desc0 + (uint64_t)(((st * 2) * L::BPART + mb * 8192 + ks * 2048) >> 4);
+              const uint64_t flo = fhi + (uint64_t)(L::BPART >> 4);
+              const uint32_t d = tb + (uint32_t)(buf * 256 + mb * 128);
+              umma_bf16_ss(d, fhi, whi, idesc, acc);
+              umma_bf16_ss(d, flo, whi, idesc, 1);
+              umma_bf16_ss(d, fhi, wlo, idesc, 1);
+            }
+            acc = 1;
+          }
+          umma_commit(&ctl.free_[st]);
+        }
+        if (nbat > 0) umma_commit(&ctl.accfull[buf]);      // every MMA of the tile has completed
+        else mbar_arrive(&ctl.accfull[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ======================= converters ============================================================
+    const int cw = warp - 2;
+    const int n0 = lane * 8;
+    const bool chan_ok = n0 < nch;
+    const uint32_t coff = (uint32_t)(n0 >> 6) * 4096u + (uint32_t)((n0 & 63) >> 3) * 16u;
+    const float *cbase = colors + ch0 + n0;
+    int gs = 0;
+    for (int k = 0;; ++k) {
+      int j, nbat;
+      tile_info(k, j, nbat);
+      if (j < 0) break;
+      for (int i = 0; i < nbat; ++i, ++gs) {
+        const int st = gs % PB_NST;
+        // the list of batch gs is only published after the MMAs of batch gs - PB_NST have released
+        // the stage: seeing it also means the B stage may be overwritten
+        mbar_wait_bounded(&ctl.list[st], (uint32_t)((gs / PB_NST) & 1));
+        const int nb = *reinterpret_cast<volatile int *>(&ctl.gcount[st]);
+        const int nbr = (nb + 15) & ~15;
+        float4 v[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = cw * 4 + r;
+          v[r][0] = v[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nb && chan_ok) {
+            const int gid = ctl.gid[st][row];
+            const float4 *src = reinterpret_cast<const float4 *>(cbase + (size_t)gid * D);
+            v[r][0] = __ldg(src);
+            v[r][1] = __ldg(src + 1);
+          }
+        }
+        unsigned char *bhi = sB + (st * 2 + 0) * L::BPART;
+        unsigned char *blo = sB + (st * 2 + 1) * L::BPART;
+        if (chan_ok) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = cw * 4 + r;
+            if (row < nbr) {
+              uint4 h, l;
+              split_pack2(v[r][0].x, v[r][0].y, h.x, l.x);
+              split_pack2(v[r][0].z, v[r][0].w, h.y, l.y);
+              split_pack2(v[r][1].x, v[r][1].y, h.z, l.z);
+              split_pack2(v[r][1].z, v[r][1].w, h.w, l.w);
+              const uint32_t off = (uint32_t)(row >> 3) * 1024u +
+                                   sw128((uint32_t)(row & 7) * 128u + (coff & 127u)) + (coff & ~127u);
+              *reinterpret_cast<uint4 *>(bhi + off) = h;
+              *reinterpret_cast<uint4 *>(blo + off) = l;
+            }
+          }
+        }
+        fence_async_smem();
+        mbar_arrive_warp(&ctl.full[st]);
+      }
+    }
+  } else {
+    // ======================= epilogue ==============================================================
+    const int ew = warp - 10;                      // 0..7
+    const int q = warp & 3;                        // the TMEM lane quarter this warp may read
+    const int sub = (ew >> 2);                     // the two warps of a quarter split the items
+    bool use_bg = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) use_bg = use_bg || (ctl.bg_nonzero[k] != 0);
+    unsigned char *boxes = sm + L::BOX_OFF + ew * 8192;
+    int nbox = 0;
+    for (int k = 0;; ++k) {
+      int j, nbat;
+      tile_info(k, j, nbat);
+      if (j < 0) break;
+      const int buf = k & 1;
+      const int by = j / tile_w, bx = j - by * tile_w;
+      const int x0 = bx * GAGS_TILE, y0 = by * 8;
+      mbar_wait_bounded(&ctl.accfull[buf], (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int idx = sub; idx < L::MB * 4; idx += 2) {
+        const int mb = idx >> 2, pc = idx & 3;
+        const int ch = mb * 128 + q * 32 + lane;
+        if (mb * 128 + q * 32 >= nch) continue;                      // warp-uniform
+        const int xb = x0 + ((pc & 1) << 3), yb = y0 + ((pc >> 1) << 2);
+        if (yb >= H || xb >= W) continue;                            // warp-uniform
+        uint32_t r[32];
+        if (nbat > 0) {
+          tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + mb * 128 + pc * 32), r);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) r[t] = 0u;
+        }
+        if (use_bg) {
+          // final transmittance of the block's 32 pixels (lane t <-> pixel t), broadcast per pixel
+          const int px = xb + (lane & 7), py = yb + (lane >> 3);
+          const float Tl = (px < W && py < H) ? 1.f - __ldg(alphas + (size_t)py * W + px) : 0.f;
+          const float b = ch < nch ? ctl.bgs[ch] : 0.f;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            r[t] = __float_as_uint(fmaf(__shfl_sync(0xffffffffu, Tl, t), b, __uint_as_float(r[t])));
+        }
+        unsigned char *box = boxes + (nbox & 1) * 4096;
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) *reinterpret_cast<uint32_t *>(box + t * 128 + lane * 4) = r[t];
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_render, box, ch0 + mb * 128 + q * 32, xb, yb);
+          bulk_commit_group();
+        }
+        ++nbox;
+      }
+      // the accumulator has been read (tcgen05.ld waited for): the MMAs of tile k + 2 may refill it
+      tc_fence_before();
+      mbar_arrive_warp(&ctl.accfree[buf]);
+      mbar_arrive_warp(&ctl.tq_free[k & (PB_TQ - 1)]);
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tb);
+}
+
+template <int NATOM>
+int launch_pers(const float *colors, int D, int ch0, int nch, const float *bg, int W, int H,
+                const int *offsets, const float *alphas, const unsigned char *wcache,
+                const int *wmeta, const int *wlist, int *wcount, float *render, cudaStream_t st) {
+  using L = PbLayout<NATOM>;
+  const int tw = (W + GAGS_TILE - 1) / GAGS_TILE;
+  const int hh = (H + 7) / 8;
+  const int ntiles = tw * hh;
+  cudaError_t e = cudaFuncSetAttribute(blend_fwd_pers<NATOM>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+  if (e != cudaSuccess) return (int)e;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (!make_render_map(&tmap, render, D, W, H)) return GAGS_EINVAL;
+  int *tilectr = wcount + ntiles;                    // the caller's extra int behind the counts
+  e = cudaMemsetAsync(tilectr, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = ntiles < gags_sm_count() ? ntiles : gags_sm_count();
+  blend_fwd_pers<NATOM><<<grid, PB_THREADS, L::BYTES, st>>>(colors, D, ch0, nch, bg, W, H, tw, ntiles,
+                                                            offsets, alphas, wcache, wmeta, wlist,
+                                                            wcount, tilectr, tmap);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// 1 = the persistent blend pass (default), 0 = one CTA per half tile
+int g_fwd_blend_persistent = 1;
+extern "C" int gags_set_blend_pass(int32_t persistent) {
+  if (persistent != 0 && persistent != 1) return GAGS_EINVAL;
+  g_fwd_blend_persistent = persistent;
+  return 0;
+}
+
+int gags_blend_fwd_from_cache_persistent(const float *colors, int32_t D, const float *background,
+                                         int32_t width, int32_t height, const int32_t *offsets,
+                                         const unsigned char *wc, const int32_t *wmeta,
+                                         const int32_t *wlist, int32_t *wcount, const float *alphas,
+                                         float *render, cudaStream_t st) {
+  for (int ch0 = 0; ch0 < D; ch0 += 256) {
+    const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
+    const int natom = (nch + 63) / 64;
+    int rc;
+#define GAGS_PB_ARGS colors, D, ch0, nch, background, width, height, offsets, alphas, wc, wmeta,   \
+                     wlist, wcount, render, st
+    switch (natom) {
+      case 1: rc = launch_pers<1>(GAGS_PB_ARGS); break;
+      case 2: rc = launch_pers<2>(GAGS_PB_ARGS); break;
+      case 3: rc = launch_pers<3>(GAGS_PB_ARGS); break;
+      default: rc = launch_pers<4>(GAGS_PB_ARGS); break;
+    }
+#undef GAGS_PB_ARGS
     if (rc != 0) return rc;
   }
   return 0;

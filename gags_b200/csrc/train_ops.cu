@@ -9,6 +9,7 @@
 //       (/root/reference/scene/gaussian_model.py:199,208 stepped at /root/reference/train.py:222-223),
 //       optionally zeroing the gradient in the same pass (zero_grad(set_to_none) analogue for a
 //       persistent gradient buffer).  Algorithmic bytes: 16 read + 12 (+4) written per element.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -769,7 +770,12 @@ extern "C" int gags_adam_lazy_rows(float *param, float *grad, float *exp_avg, fl
   c.omb1 = (float)(1.0 - beta1); c.omb2 = (float)(1.0 - beta2);
   c.eps = (float)eps;
   long long blocks = (rows + 255) / 256;                       // one row per lane-slot of flags
-  const long long cap = (long long)gags_sm_count() * 8;
+  static int lazy_ctas = -1;                                   // tuning: GAGS_B200_LAZY_GRID=CTAs/SM
+  if (lazy_ctas < 0) {
+    const char *e = getenv("GAGS_B200_LAZY_GRID");
+    lazy_ctas = (e && atoi(e) > 0 && atoi(e) <= 32) ? atoi(e) : 8;
+  }
+  const long long cap = (long long)gags_sm_count() * lazy_ctas;
   if (blocks > cap) blocks = cap;
   adam_lazy_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(
       reinterpret_cast<float4 *>(param), reinterpret_cast<float4 *>(grad),

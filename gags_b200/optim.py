@@ -92,13 +92,20 @@ class LazyRows:
         self.consts[first:step + 1].copy_(self._host[first:step + 1], non_blocking=True)
         self.t = step
 
-    def _launch(self, grad, flags, t_to: int, t_apply: int, clear: bool) -> None:
+    def _launch(self, grad, flags, t_to: int, t_apply: int, clear: bool, r0: int = 0,
+                r1: int = None) -> None:
+        """Rows [r0, r1) only (default: all)."""
         p = self.param
+        r1 = self.rows if r1 is None else r1
+        if r1 <= r0:
+            return
+        off = 4 * r0 * self.dim
         _C.check(_C.lib.gags_adam_lazy_rows(
-            p.data_ptr(), _C.ptr(grad), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-            _C.ptr(flags), self.last.data_ptr(), self.consts.data_ptr(), self.rows, self.dim,
-            int(t_to), int(t_apply), self.betas[0], self.betas[1], self.eps, 1 if clear else 0,
-            _C.stream_ptr()), "gags_adam_lazy_rows")
+            p.data_ptr() + off, None if grad is None else grad.data_ptr() + off,
+            self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off,
+            None if flags is None else flags.data_ptr() + r0, self.last.data_ptr() + 4 * r0,
+            self.consts.data_ptr(), r1 - r0, self.dim, int(t_to), int(t_apply), self.betas[0],
+            self.betas[1], self.eps, 1 if clear else 0, _C.stream_ptr()), "gags_adam_lazy_rows")
         _C.count_launch()
 
     @torch.no_grad()
@@ -108,11 +115,16 @@ class LazyRows:
             self._launch(None, flags, self.t, 0, False)
 
     @torch.no_grad()
-    def apply(self, grad, flags, step: int, lr: float) -> None:
+    def apply(self, grad, flags, step: int, lr: float, r0: int = 0, r1: int = None) -> None:
         """Optimiser step `step` on the flagged rows only (caught up first, gradient re-zeroed, flags
-        cleared); every other row falls one more step behind."""
-        self.record_step(step, lr)
-        self._launch(grad, flags, step - 1, step, True)
+        cleared); every other row falls one more step behind.  With a row range [r0, r1) the step is
+        applied piecewise (SparsePeerAdam overlaps the pieces with the exchange of the next ones):
+        the first piece of a step records it."""
+        if step == self.t + 1:
+            self.record_step(step, lr)
+        elif step != self.t:
+            raise RuntimeError("LazyRows.apply: steps must be taken in order")
+        self._launch(grad, flags, step - 1, step, True, r0, r1)
         self.behind = True
 
     @torch.no_grad()

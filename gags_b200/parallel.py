@@ -346,7 +346,20 @@ class SparsePeerAdam:
         self._mc_grad = mc if self.multicast else None
         self._mc_flags = (mc + 4 * numel) if self.multicast else None
         self._xstream = torch.cuda.Stream(device=dev, priority=-1)
+        self._ustream = torch.cuda.Stream(device=dev, priority=-1)       # the local update pass
         self._done = None
+        # row ranges processed as a pipeline (exchange of range c+1 beside the update of range c);
+        # boundaries on flag words, per-range pointer tables for the peers' buffers
+        self.chunks = max(1, int(os.environ.get("GAGS_B200_EXCHANGE_CHUNKS", "4")))
+        wc = -(-self.words // self.chunks) if self.words else 0
+        self._chunk_args = []
+        for c in range(self.chunks):
+            r0, r1 = min(self.rows, 4 * wc * c), min(self.rows, 4 * wc * (c + 1))
+            if r1 <= r0:
+                continue
+            gp = (ctypes.c_uint64 * self.world)(*[b + 4 * r0 * self.dim for b in base])
+            fp = (ctypes.c_uint64 * self.world)(*[b + 4 * numel + r0 for b in base])
+            self._chunk_args.append((r0, r1, gp, fp))
         self.exp_avg = torch.zeros_like(param, memory_format=torch.preserve_format)
         self.exp_avg_sq = torch.zeros_like(param, memory_format=torch.preserve_format)
         param.grad = self.grad
@@ -365,10 +378,12 @@ class SparsePeerAdam:
 
     @torch.no_grad()
     def step(self) -> None:
-        """Enqueue exchange + update on their own stream behind everything the current stream has
+        """Enqueue exchange + update on their own streams behind everything the current stream has
         queued (the backward); the current stream goes on with the next view's projection / tile
-        sort, and the next forward blend / backward wait for the update through
-        rasterization.param_ready_events / sink_ready_events."""
+        sort / weights pass, and the next blend pass / backward wait for the update through
+        rasterization.param_ready_events / sink_ready_events.  The table is processed in
+        `self.chunks` row ranges: while the fabric sums the rows of range c+1, the HBM-bound local
+        Adam pass already runs on range c (a second stream)."""
         C, R = self._C, self._R
         p = self.param
         if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr():
@@ -377,48 +392,67 @@ class SparsePeerAdam:
         self.step_count += 1
         dev = p.device
         main = torch.cuda.current_stream(dev)
-        xs = self._xstream
+        xs, us = self._xstream, self._ustream
         ev_b = torch.cuda.Event()
         ev_b.record(main)
         xs.wait_event(ev_b)
+        ev = None
+        if self.timing is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         with torch.cuda.stream(xs):
-            ev = None
-            if self.timing is not None:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            if ev:
                 ev[0].record(xs)
             self._hdl.barrier()                           # every rank's backward has finished
             if ev:
                 ev[1].record(xs)
-            C.check(C.lib.gags_grad_allreduce_rows(
-                self.world, self.rank, self._grad_ptrs, self._flag_ptrs, self._mc_grad,
-                self._mc_flags, C.ptr(self.union_flags), self.rows, self.dim, xs.cuda_stream),
-                "gags_grad_allreduce_rows")
-            C.count_launch()
+        for c, (r0, r1, gp, fp) in enumerate(self._chunk_args):
+            last = c == len(self._chunk_args) - 1
+            with torch.cuda.stream(xs):
+                off = 4 * r0 * self.dim
+                C.check(C.lib.gags_grad_allreduce_rows(
+                    self.world, self.rank, gp, fp,
+                    None if self._mc_grad is None else self._mc_grad + off,
+                    None if self._mc_flags is None else self._mc_flags + r0,
+                    self.union_flags.data_ptr() + r0, r1 - r0, self.dim, xs.cuda_stream),
+                    "gags_grad_allreduce_rows")
+                C.count_launch()
+                if ev and last:
+                    ev[2].record(xs)
+                self._hdl.barrier()                       # every replica holds this range's sums
+                if ev and last:
+                    ev[3].record(xs)
+                summed = torch.cuda.Event()
+                summed.record(xs)
+                if last:                                  # every rank has read every rank's flags
+                    C.check(C.lib.gags_memset_zero(C.ptr(self._flag_bytes), 4 * self.words,
+                                                   xs.cuda_stream), "gags_memset_zero")
+                    cleared = torch.cuda.Event()
+                    cleared.record(xs)
+            us.wait_event(summed)
+            with torch.cuda.stream(us):
+                if self.lz is not None:
+                    self.lz.apply(self.grad, self.union_flags, self.step_count, self.lr, r0, r1)
+                else:
+                    off = 4 * r0 * self.dim
+                    C.check(C.lib.gags_adam_step_rows(
+                        p.data_ptr() + off, self.grad.data_ptr() + off,
+                        self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off,
+                        self.union_flags.data_ptr() + r0, r1 - r0, self.dim, self.lr, self.betas[0],
+                        self.betas[1], self.eps, self.step_count, us.cuda_stream),
+                        "gags_adam_step_rows")
+                    C.count_launch()
+        us.wait_event(cleared)
+        with torch.cuda.stream(us):
             if ev:
-                ev[2].record(xs)
-            self._hdl.barrier()                           # every replica holds the sums; flags read
-            if ev:
-                ev[3].record(xs)
-            if self.lz is not None:
-                self.lz.apply(self.grad, self.union_flags, self.step_count, self.lr)
-            else:
-                C.check(C.lib.gags_adam_step_rows(
-                    p.data_ptr(), self.grad.data_ptr(), C.ptr(self.exp_avg), C.ptr(self.exp_avg_sq),
-                    C.ptr(self.union_flags), self.rows, self.dim, self.lr, self.betas[0],
-                    self.betas[1], self.eps, self.step_count, xs.cuda_stream), "gags_adam_step_rows")
-            C.check(C.lib.gags_memset_zero(C.ptr(self._flag_bytes), 4 * self.words, xs.cuda_stream),
-                    "gags_memset_zero")
-            C.count_launch()
-            if ev:
-                ev[4].record(xs)
+                ev[4].record(us)
                 self.timing.append(ev)
                 if len(self.timing) > 64:
                     del self.timing[:-64]
             done = torch.cuda.Event()
-            done.record(xs)
+            done.record(us)
         self._done = done
         self._rf.dirty = False
-        R.param_ready_events[p.data_ptr()] = done         # the next forward blend waits for this
+        R.param_ready_events[p.data_ptr()] = done         # the next blend pass waits for this
         R.sink_ready_events[self.grad.data_ptr()] = done  # ... and so does the next backward
         p.grad = self.grad
 

@@ -377,6 +377,11 @@ int gags_set_peer_unroll(int32_t unroll);
  * epilogue.  Bit-identical outputs; process-wide; used by the parity tests and bench.             */
 int gags_set_fwd_variant(int32_t variant);
 
+/* Tuning hook: 1 (default) = gags_blend_fwd_from_cache as ONE persistent CTA per SM (double-buffered
+ * TMEM accumulators: the epilogue of a half tile overlaps the MMAs of the next), 0 = one CTA per half
+ * tile.  Bit-identical outputs; process-wide.                                                     */
+int gags_set_blend_pass(int32_t persistent);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);

@@ -1050,13 +1050,21 @@ def test_two_pass_forward_equals_single_pass():
         _C.check(_C.lib.gags_blend_fwd_weights(_C.ptr(st["geom"]), W, H, _C.ptr(st["offsets"]),
                                                _C.ptr(st["flatten_ids"]), _C.ptr(a1), _C.ptr(l1),
                                                *[_C.ptr(x) for x in c1], s))
-        _C.check(_C.lib.gags_blend_fwd_from_cache(_C.ptr(cols), D, _C.ptr(bgc), W, H,
-                                                  _C.ptr(st["offsets"]), *[_C.ptr(x) for x in c1],
-                                                  _C.ptr(a1), _C.ptr(r1), s))
-        torch.cuda.synchronize()
         assert torch.equal(a0, a1) and (with_bg or torch.equal(l0, l1))
         assert torch.equal(c0[3][:n_half], c1[3][:n_half]) and int(c1[3][:n_half].sum()) > 0
-        assert torch.equal(r0, r1)
+        # both forms of the blend pass: one persistent CTA per SM (default), one CTA per half tile
+        try:
+            for persistent in (1, 0):
+                assert _C.lib.gags_set_blend_pass(persistent) == 0
+                r1.fill_(float("nan"))
+                _C.check(_C.lib.gags_blend_fwd_from_cache(_C.ptr(cols), D, _C.ptr(bgc), W, H,
+                                                          _C.ptr(st["offsets"]),
+                                                          *[_C.ptr(x) for x in c1], _C.ptr(a1),
+                                                          _C.ptr(r1), s))
+                torch.cuda.synchronize()
+                assert torch.equal(r0, r1), (D, persistent)
+        finally:
+            _C.lib.gags_set_blend_pass(1)
     assert _C.lib.gags_blend_fwd_weights(None, 4, 4, None, None, None, None, None, None, None, None,
                                          _C.stream_ptr()) != 0
     assert _C.lib.gags_blend_fwd_from_cache(None, 64, None, 4, 4, None, None, None, None, None, None,
