@@ -455,10 +455,11 @@ def main():
         peak_kind = "measured" if peaks else "fallback"
         acc = {}
         reps = 5
-        saved_direct = R.direct_grad_accumulation
         if peer is not None:
-            R.direct_grad_accumulation = False     # the instrumented single-GPU pass uses its own buffer
-            pc._semantic_feature.grad = None
+            # the instrumented passes run this rank's own pipeline (same buffers, same kernels as the
+            # timed loop) without the exchange: the gradient is dropped after each pass
+            peer.synchronize()
+            peer.reset_grad()
         for i in range(-3, reps):                 # three unrecorded passes: this single-stream,
             R.stage_events = []                   # instrumented path has its own allocation pattern
             cam = cams[(7 * i) % n_views]
@@ -484,7 +485,7 @@ def main():
                     R._mark("adam")
                     pc.optimizer.zero_grad(set_to_none=True)
                 else:
-                    pc._semantic_feature.grad = None
+                    peer.reset_grad()
             torch.cuda.synchronize()
             ev = R.stage_events
             R.stage_events = None
@@ -495,9 +496,6 @@ def main():
             if i == 0:
                 radii = pkg["radii"]
                 stats["n_visible"] = int((radii > 0).sum())
-        if peer is not None:
-            R.direct_grad_accumulation = saved_direct
-            pc._semantic_feature.grad = peer.grad
         # min over the repetitions: a cudaMalloc that lands inside one instrumented pass (this path
         # allocates differently from the timed loop) must not be booked as kernel time
         stage_ms = {k: min(v) for k, v in acc.items()}
@@ -544,8 +542,17 @@ def main():
                 "achieved_GBps_of_the_pair": (nv * 4 * D + H * W * (4 * D + 8)) / (t2 * 1e-3) / 1e9,
                 "note": "algorithmic bytes of the whole forward (N_vis*4D + H*W*(4D+8)) over the sum "
                         "of the passes incl. the catch-up of the rows the view reads"}
-            if kname == "blend_fwd":
-                roofline["traffic"] = None               # the committed capture is of the single pass
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))) if cfg in (3, 4) else {}
+            except Exception:
+                tj = {}
+            bp_bytes = nv * 4 * D + H * W * 4 * D
+            bp = bp_bytes / (stage_ms["blend_fwd"] * 1e-3) / 1e9
+            roofline["forward_blend_pass"] = {
+                "kernel": "blend_fwd_pers (render = cached weights x features)",
+                "algorithmic_bytes": bp_bytes, "avg_launch_ms": stage_ms["blend_fwd"],
+                "achieved": bp, "frac": bp / hbm_peak, "traffic": tj.get("blend_fwd"),
+                "weights_pass_traffic": tj.get("fwd_weights")}
         if fwd_only:
             step_bytes = n * (44 + 4 * D) + H * W * (4 * D + 4)
         else:
@@ -658,10 +665,19 @@ def dense_target_leg(env):
     k = max(5, args.steps // 2)
     for i in range(3):
         step_dense(i)
+    # two repetitions, the faster one counts: this leg's 2 GB temporaries (gradient map, target) make
+    # the caching allocator call cudaMalloc inside the first timed region now and then (a ~100 ms
+    # device-wide stall that is not part of the workload; `diag` shows the slowest step)
     ms_d, _, _, _ = timed(step_dense, k, 2)
+    diag = dict(timed.diag)
+    ms_d2, _, _, _ = timed(step_dense, k, 0)
+    if ms_d2 < ms_d:
+        ms_d, diag = ms_d2, dict(timed.diag)
+    timed.diag = diag
     out = {"value": k / (ms_d * 1e-3), "unit": "views/s",
            "workload": "dense N(0,0.1^2) [H,W,D] target (SURVEY App. B), l1_loss_fused + autograd "
-                       "backward (cached weights) + fused Adam"}
+                       "backward (cached weights) + fused Adam",
+           "diag": dict(timed.diag)}
     if not args.no_e2e:
         ke = max(3, args.steps // 4)
         ms_e, _, _, _ = timed(step_dense_e2e, ke, 1)

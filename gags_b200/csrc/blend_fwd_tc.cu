@@ -771,6 +771,20 @@ bool make_render_map(CUtensorMap *m, float *render, int D, int W, int H) {
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the same raster with a (256 channels x 8 pixels x 4 rows) box: a pixel's whole 1 KB row leaves in
+// one piece (persistent blend pass, D % 256 == 0 channel blocks)
+bool make_render_map_wide(CUtensorMap *m, float *render, int D, int W, int H) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (D & 3) || D < 256 || !gags_aligned16(render)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)W, (cuuint64_t)H};
+  const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)W * D * 4};
+  const cuuint32_t box[3] = {256, 8, 4};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, render, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NATOM, bool V3, int MODE = 0>
 int launch_tc(const float *geom, const float *colors, int D, int ch0, int nch, const float *bg, int W,
               int H, const int *offsets, const int *ids, float *render, float *alphas,
@@ -956,7 +970,8 @@ blend_fwd_pers(const float *__restrict__ colors, int D, int ch0, int nch,
                const int *__restrict__ offsets, const float *__restrict__ alphas,
                const unsigned char *__restrict__ wcache, const int *__restrict__ wmeta,
                const int *__restrict__ wlist, const int *__restrict__ wcount,
-               int *__restrict__ tilectr, const __grid_constant__ CUtensorMap tmap_render) {
+               int *__restrict__ tilectr, const __grid_constant__ CUtensorMap tmap_render,
+               const __grid_constant__ CUtensorMap tmap_wide, int use_wide) {
   using L = PbLayout<NATOM>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1175,6 +1190,46 @@ blend_fwd_pers(const float *__restrict__ colors, int D, int ch0, int nch,
       const int x0 = bx * GAGS_TILE, y0 = by * 8;
       mbar_wait_bounded(&ctl.accfull[buf], (uint32_t)((k >> 1) & 1));
       tc_fence_after();
+      if (NATOM == 4 && use_wide) {
+        // 256 channels: the eight warps are the eight (128-channel block, lane quarter) pairs, so
+        // together they hold every channel of a 8x4 pixel block — staged as [32 px][256 ch] and
+        // stored by ONE tensor store per block: each pixel's 1 KB row reaches DRAM in one piece
+        const int mb = sub;
+        const int ch = mb * 128 + q * 32 + lane;
+        unsigned char *wide = sm + L::BOX_OFF;
+#pragma unroll 1
+        for (int pc = 0; pc < 4; ++pc) {
+          const int xb = x0 + ((pc & 1) << 3), yb = y0 + ((pc >> 1) << 2);
+          if (yb >= H || xb >= W) continue;                          // uniform over the 8 warps
+          uint32_t r[32];
+          if (nbat > 0) {
+            tmem_ld_32x32(tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + mb * 128 + pc * 32), r);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) r[t] = 0u;
+          }
+          if (use_bg) {
+            const int px = xb + (lane & 7), py = yb + (lane >> 3);
+            const float Tl = (px < W && py < H) ? 1.f - __ldg(alphas + (size_t)py * W + px) : 0.f;
+            const float b = ctl.bgs[ch];
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              r[t] = __float_as_uint(fmaf(__shfl_sync(0xffffffffu, Tl, t), b, __uint_as_float(r[t])));
+          }
+          unsigned char *box = wide + (nbox & 1) * 32768;
+          if (ew == 0 && lane == 0) bulk_wait_group_read<1>();      // the box's previous store has read it
+          named_bar_sync(1, 256);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) *reinterpret_cast<uint32_t *>(box + t * 1024 + ch * 4) = r[t];
+          fence_async_smem();
+          named_bar_sync(2, 256);
+          if (ew == 0 && lane == 0) {
+            tma_store_3d(&tmap_wide, box, ch0, xb, yb);
+            bulk_commit_group();
+          }
+          ++nbox;
+        }
+      } else {
 #pragma unroll 1
       for (int idx = sub; idx < L::MB * 4; idx += 2) {
         const int mb = idx >> 2, pc = idx & 3;
@@ -1211,6 +1266,7 @@ blend_fwd_pers(const float *__restrict__ colors, int D, int ch0, int nch,
         }
         ++nbox;
       }
+      }
       // the accumulator has been read (tcgen05.ld waited for): the MMAs of tile k + 2 may refill it
       tc_fence_before();
       mbar_arrive_warp(&ctl.accfree[buf]);
@@ -1238,13 +1294,16 @@ int launch_pers(const float *colors, int D, int ch0, int nch, const float *bg, i
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!make_render_map(&tmap, render, D, W, H)) return GAGS_EINVAL;
+  CUtensorMap tmapw;
+  memset(&tmapw, 0, sizeof(tmapw));
+  const int use_wide = (NATOM == 4 && nch == 256 && make_render_map_wide(&tmapw, render, D, W, H)) ? 1 : 0;
   int *tilectr = wcount + ntiles;                    // the caller's extra int behind the counts
   e = cudaMemsetAsync(tilectr, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   const int grid = ntiles < gags_sm_count() ? ntiles : gags_sm_count();
   blend_fwd_pers<NATOM><<<grid, PB_THREADS, L::BYTES, st>>>(colors, D, ch0, nch, bg, W, H, tw, ntiles,
                                                             offsets, alphas, wcache, wmeta, wlist,
-                                                            wcount, tilectr, tmap);
+                                                            wcount, tilectr, tmap, tmapw, use_wide);
   return (int)cudaGetLastError();
 }
 

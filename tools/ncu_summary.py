@@ -80,7 +80,9 @@ def full(src, dst):
         name = short(r[hdr.index("Kernel Name")])
         # blend_fwd_tc<NATOM, V3, MODE>: MODE 1 = weights pass, 2 = blend pass, 0 = single pass
         key = None
-        if "blend_fwd" in name:
+        if "blend_fwd_pers" in name:
+            key = "blend_fwd"                                   # the persistent blend pass
+        elif "blend_fwd" in name:
             mode = name.rstrip("> ").split(",")[-1].strip() if "<" in name else "0"
             key = {"1": "fwd_weights", "2": "blend_fwd"}.get(mode, "blend_fwd_single")
         elif "blend_bwd" in name:
