@@ -63,7 +63,7 @@ constexpr int TC_THREADS = 448;   // 13 role warps + the weight-tile store warp
 // + the store warp, three CTAs per SM
 template <int MODE> struct TcCfg {
   static constexpr int THREADS = MODE == 1 ? 288 : TC_THREADS;
-  static constexpr int MINB = MODE == 1 ? 3 : 2;
+  static constexpr int MINB = MODE == 1 ? 4 : 2;
   static constexpr int NCW = MODE == 2 ? 8 : 4;      // converter warps (MODE 2: the chain warps too)
 };
 
@@ -878,7 +878,7 @@ extern "C" int gags_blend_fwd_weights(const float *geom, int32_t width, int32_t 
     return GAGS_EINVAL;
   if (g_gags_blend_impl == 1) return GAGS_EINVAL;
   if (!gags_aligned16(geom) || !gags_aligned16(wcache)) return GAGS_EALIGN;
-  return launch_tc<1, true, 1>(geom, nullptr, 64, 0, 64, nullptr, width, height, offsets,
+  return launch_tc<0, true, 1>(geom, nullptr, 64, 0, 64, nullptr, width, height, offsets,
                                flatten_ids, nullptr, alphas, last_ids,
                                reinterpret_cast<unsigned char *>(wcache), wmeta, wlist, wcount,
                                (cudaStream_t)stream);

@@ -51,6 +51,7 @@ class LazyRows:
         self._host = torch.zeros(self.cap, 2, dtype=torch.float32).pin_memory()
         self.behind = False                          # some row may be behind step t
         self.flags = None                            # set by the owner: RowFlags of the gradient
+        self.pending = None                          # event of the last launch made on another stream
         R.lazy_owners[param.data_ptr()] = self
 
     def release(self) -> None:
@@ -99,6 +100,8 @@ class LazyRows:
         r1 = self.rows if r1 is None else r1
         if r1 <= r0:
             return
+        if self.pending is not None:                 # a step still running on its own stream
+            torch.cuda.current_stream(p.device).wait_event(self.pending)
         off = 4 * r0 * self.dim
         _C.check(_C.lib.gags_adam_lazy_rows(
             p.data_ptr() + off, None if grad is None else grad.data_ptr() + off,
@@ -127,9 +130,15 @@ class LazyRows:
         self._launch(grad, flags, step - 1, step, True, r0, r1)
         self.behind = True
 
+    def wait(self) -> None:
+        """Order the current stream behind a step that runs on its own stream."""
+        if self.pending is not None:
+            torch.cuda.current_stream(self.param.device).wait_event(self.pending)
+
     @torch.no_grad()
     def flush(self) -> None:
         """Every row up to the current step: afterwards the tensors are what the dense pass holds."""
+        self.wait()
         if self.behind:
             self._launch(None, None, self.t, 0, False)
             self.behind = False
@@ -143,6 +152,9 @@ class FusedAdam(torch.optim.Optimizer):
         self.lazy_rows = bool(lazy_rows)
         self._rows = {}                     # id(param) -> (persistent grad buffer, RowFlags)
         self._lazy = {}                     # id(param) -> LazyRows
+        self._ustreams = {}                 # device index -> stream of the lazily evaluated step
+        import os
+        self.async_step = os.environ.get("GAGS_B200_ASYNC_ADAM", "1") != "0"
 
     # ---- row-sparse gradient bookkeeping ---------------------------------------------------------
     def _sparse_ok(self, p) -> bool:
@@ -196,7 +208,9 @@ class FusedAdam(torch.optim.Optimizer):
                 rows = self._rows.get(id(p))
                 if rows is not None and p.grad is not None \
                         and p.grad.data_ptr() == rows[0].data_ptr():
-                    self._check_dense_writes(rows)
+                    if (rows[0]._version != rows[2] or rows[1].dirty) and id(p) in self._lazy:
+                        self._lazy[id(p)].wait()      # only when device work follows: the usual
+                    self._check_dense_writes(rows)    # step(); zero_grad() pair stays asynchronous
                     if rows[1].dirty:
                         p.grad.zero_()
                         rows[1].flags.zero_()
@@ -241,7 +255,29 @@ class FusedAdam(torch.optim.Optimizer):
                             lz.record_until(t - 1, lr)
                             lz.last.fill_(t - 1)
                             lz.flags = rows[1]
-                        lz.apply(p.grad, rows[1].flags, t, lr)
+                        # The step runs on its own stream: it touches ~7 % of the rows and nothing
+                        # the next view's projection / tile sort / weights pass reads, so those
+                        # start right behind the backward; the next blend pass and backward wait
+                        # for it through rasterization's events, flush() / state_dict() do too.
+                        from . import rasterization as R
+                        if R.stage_events is not None or not self.async_step:
+                            lz.apply(p.grad, rows[1].flags, t, lr)     # (instrumented: in line)
+                        else:
+                            dev = p.device
+                            us = self._ustreams.get(dev.index)
+                            if us is None:
+                                us = self._ustreams[dev.index] = torch.cuda.Stream(device=dev,
+                                                                                   priority=-1)
+                            ev0 = torch.cuda.Event()
+                            ev0.record(torch.cuda.current_stream(dev))
+                            us.wait_event(ev0)
+                            with torch.cuda.stream(us):
+                                lz.apply(p.grad, rows[1].flags, t, lr)
+                                done = torch.cuda.Event()
+                                done.record(us)
+                            lz.pending = done
+                            R.param_ready_events[p.data_ptr()] = done
+                            R.sink_ready_events[p.grad.data_ptr()] = done
                     else:
                         _C.check(_C.lib.gags_adam_step_rows(
                             p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(),

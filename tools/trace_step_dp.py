@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-level timeline of the view-parallel training step (torch.profiler / CUPTI) on rank 0:
-start, duration, stream of every kernel of three steps with parallel.PeerAdam.
+start, duration, stream of every kernel of four steps with parallel.SparsePeerAdam (TRACE_DENSE=1: PeerAdam).
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/trace_step_dp.py"""
 import json, os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,7 +29,7 @@ g = torch.Generator().manual_seed(1)
 seg = torch.randint(0, 256, (1080, 1920), generator=g, dtype=torch.int32).to(dev)
 emb = (0.1 * torch.randn(256, 256, generator=g)).to(dev)
 grp = pc.optimizer.param_groups[0]
-peer = parallel.PeerAdam(pc._semantic_feature, lr=grp["lr"], betas=grp["betas"], eps=grp["eps"])
+peer = (parallel.PeerAdam if os.environ.get("TRACE_DENSE") else parallel.SparsePeerAdam)(pc._semantic_feature, lr=grp["lr"], betas=grp["betas"], eps=grp["eps"])
 def step(i):
     v = parallel.views_for_rank(i, rank, world, 1, 64)[0]
     pkg = render(cams[v], pc, None, bg)
