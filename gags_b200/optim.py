@@ -78,6 +78,8 @@ class LazyRows:
         host[:self._host.shape[0]] = self._host
         dev = torch.zeros(self.cap, 2, dtype=torch.float32, device=self.consts.device)
         dev[:self.consts.shape[0]] = self.consts
+        # kernels on other streams may still read the old table: keep it alive (a few KB)
+        self._retired = getattr(self, "_retired", []) + [self.consts, self._host]
         self._host, self.consts = host, dev
 
     def record_until(self, step: int, lr: float) -> None:

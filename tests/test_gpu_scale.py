@@ -621,3 +621,67 @@ def test_kat_culls_and_background_replication():
     diff = img - blk                                   # = T_final * bg, identical in every channel
     assert float(diff.max()) > 0.5
     assert float((diff - diff[0:1]).abs().max()) < 1e-6
+
+
+def test_benchmark_config_lazy_two_pass_training_path():
+    """BASELINE config 3 at full size through the training fast path bench.py times: four optimiser
+    steps (views 0..3) with the persistent gradient + row flags, the two-pass forward (weights pass,
+    catch-up of the rows the view reads, persistent blend pass), the loss fused into the cached
+    backward and the lazily evaluated Adam step on its own stream.  A shadow table takes the DENSE
+    kernel's step on the same gradients.  Checked: (1) the render of step 4 — produced from a table
+    in which most rows are behind — equals, bit for bit, a no-cache single-pass render of the shadow
+    table (the single-pass render is what test_benchmark_config_parity_on_sampled_tiles pins to the
+    fp64 oracle); (2) the flagged rows cover the gradient and are a small part of the table; (3)
+    after flush() parameters and both moments are bit-identical to the dense optimiser's on all
+    2 M x 256 entries."""
+    from gags_b200 import _C
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.synthetic import CONFIGS, config_scene
+    from gags_b200.utils.loss_utils import l1_backward_fused
+    dev = torch.device("cuda:0")
+    n, H, W, D = CONFIGS[3]
+    scene = config_scene(3)
+    pc = _model(scene, dev)
+    opt, p = pc.optimizer, pc._semantic_feature
+    assert opt.lazy_rows and opt.sparse_rows
+    grp = opt.param_groups[0]
+    lr, (b1, b2), eps = grp["lr"], grp["betas"], grp["eps"]
+    g = torch.Generator().manual_seed(4321)
+    seg = torch.randint(0, 256, (H // 8 + 1, W // 8 + 1), generator=g, dtype=torch.int32) \
+        .repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].contiguous().to(dev)
+    emb = (0.1 * torch.randn(256, D, generator=g)).to(dev)
+    bg = torch.zeros(3, device=dev)
+    ps = p.detach().clone()
+    ms, vs = torch.zeros_like(ps), torch.zeros_like(ps)
+    shadow = _model(scene, dev)
+    last = None
+    for it in range(1, 5):
+        cam = scene.cameras[it - 1].to(dev)
+        pkg = render(cam, pc, None, bg)
+        if it == 4:
+            shadow._semantic_feature.data.copy_(ps)
+            with torch.no_grad():
+                ref = render(cam, shadow, None, bg)["render"]
+            assert torch.equal(pkg["render"].detach(), ref)
+            last = pkg["render"].detach().permute(1, 2, 0).clone()
+            lz = opt._lazy[id(p)]
+            assert lz.behind and int((lz.last < 3).sum()) > n // 2        # most rows are behind
+        l1_backward_fused(pkg["render"], seg, emb)
+        gcopy = p.grad.clone()
+        rows = opt._rows.get(id(p))
+        if rows is not None and it >= 2:
+            nz = gcopy.abs().amax(dim=1) > 0
+            fl = rows[1].flags.bool()
+            assert bool((fl | ~nz).all()) and 0.02 < float(fl.float().mean()) < 0.2
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        _C.check(_C.lib.gags_adam_step(ps.data_ptr(), gcopy.data_ptr(), ms.data_ptr(), vs.data_ptr(),
+                                       ps.numel(), float(lr), float(b1), float(b2), float(eps), it, 0,
+                                       _C.stream_ptr()))
+        del gcopy
+    assert bool(torch.isfinite(last).all())
+    opt.flush()
+    torch.cuda.synchronize()
+    st = opt.state[p]
+    assert torch.equal(p.detach(), ps)
+    assert torch.equal(st["exp_avg"], ms) and torch.equal(st["exp_avg_sq"], vs)
