@@ -88,6 +88,7 @@ SIGNATURES = {
     "gags_set_peer_grid": (C.c_int, [_i32]),
     "gags_set_fwd_variant": (C.c_int, [_i32]),
     "gags_set_blend_pass": (C.c_int, [_i32]),
+    "gags_set_bwd_sign_operand": (C.c_int, [_i32]),
     "gags_set_peer_unroll": (C.c_int, [_i32]),
     "gags_adam_step_peer": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _i64, C.c_double,
                                       C.c_double, C.c_double, C.c_double, _i32, _p]),
@@ -115,6 +116,9 @@ for _env, _fn in (("GAGS_B200_PEER_GRID", "gags_set_peer_grid"),
 if os.environ.get("GAGS_B200_BLEND_IMPL"):           # 0 auto, 1 SIMT only, 2 tensor-core required
     if lib.gags_set_blend_impl(int(os.environ["GAGS_B200_BLEND_IMPL"])) != 0:
         raise ValueError("GAGS_B200_BLEND_IMPL must be 0, 1 or 2")
+if os.environ.get("GAGS_B200_BWD_SIGN"):             # 1 exact sign operand (default), 0 hi / lo split
+    if lib.gags_set_bwd_sign_operand(int(os.environ["GAGS_B200_BWD_SIGN"])) != 0:
+        raise ValueError("GAGS_B200_BWD_SIGN must be 0 or 1")
 if os.environ.get("GAGS_B200_BLEND_PASS"):            # 1 persistent (default), 0 one CTA per half tile
     if lib.gags_set_blend_pass(int(os.environ["GAGS_B200_BLEND_PASS"])) != 0:
         raise ValueError("GAGS_B200_BLEND_PASS must be 0 or 1")

@@ -49,7 +49,7 @@ constexpr int CB_THREADS = 320;   // warps 0-3 v_render staging, 4-7 epilogue, 8
 constexpr int CB_JQ = 8;          // job-id ring (roles are never more than 4 jobs apart, see below)
 
 struct CbCtl {
-  uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull, vfree;
+  uint64_t wfull[2], wfree[2], accfull[2], accfree[2], vfull[2], vfree[2];
   uint64_t jq_full[CB_JQ];
   uint32_t tmem_base;
   int jobq[CB_JQ];
@@ -118,7 +118,13 @@ struct CbL1 {
   long long hw;
 };
 
-template <int LM>
+// SGN (LM = 1 without a pixel mask): the L1 gradient is scale * sign(render - target) with ONE scale
+// for the whole image, so the staged operand is the sign itself — exactly representable in bf16:
+// no lo part to compute, store or multiply (half the staging stores, half the MMAs), and the scale
+// is applied once to the accumulator in the epilogue.  More accurate than the hi / lo split of
+// scale * sign (whose 2^-17 representation error is the same for every pixel and does not average
+// out), hence the 1e-5 agreement the tests ask between the fused and the two-kernel route.
+template <int LM, bool SGN = false>
 __global__ void __launch_bounds__(CB_THREADS, 2)
 blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, long long njobs,
                  const int *__restrict__ offsets, const unsigned char *__restrict__ wcache,
@@ -151,8 +157,10 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
       mbar_init(&ctl.accfull[k], 1);
       mbar_init(&ctl.accfree[k], 4);               // epilogue warps
     }
-    mbar_init(&ctl.vfull, 4);                      // staging warps
-    mbar_init(&ctl.vfree, 1);                      // tcgen05.commit after a job's last MMA
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&ctl.vfull[k], 4);                 // staging warps
+      mbar_init(&ctl.vfree[k], 1);                 // tcgen05.commit after a job's last MMA
+    }
     for (int k = 0; k < CB_JQ; ++k) mbar_init(&ctl.jq_full[k], 1);
     mbar_fence_init();
   }
@@ -172,7 +180,9 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
     const int q = warp;                             // pixel block (8x4) of the half tile
     const int n0 = (lane & 15) * 8;                 // lane l owns channels [8 (l & 15), +8) of pixel
     const uint32_t coff = (uint32_t)((n0 >> 6) & 1) * 16384u + (uint32_t)((n0 & 63) >> 3) * 16u;
-    unsigned char *vhi = sV, *vlo = sV + L::VPART;
+    // SGN: one bf16 part per job, so the hi | lo space holds TWO jobs' operands — job k + 1 is staged
+    // while the MMAs of job k still read theirs (the staging warps never wait for the job in flight)
+    constexpr int NVB = SGN ? 2 : 1;
     int jn = 0;                                     // non-empty jobs staged so far
     float l1acc = 0.f;
     for (int k = 0;; ++k) {
@@ -258,7 +268,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
           if (round + 1 < 16 / PJ) load_seg(round + 1);
 #pragma unroll
           for (int jj = 0; jj < PJ; ++jj) {
-            const float sc = l1.scale * mk[jj];
+            const float sc = SGN ? (mk[jj] != 0.f ? 1.f : 0.f) : l1.scale * mk[jj];
             float part = 0.f;
             float vs[NL];
 #pragma unroll
@@ -271,7 +281,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
                           fmaf(wl[jj][1 % NL], t[jj][1 % NL][h].c, wl[jj][0] * tg));            \
               const float d = v[jj][h].c - tg;                                                 \
               part += fabsf(d);                                                                \
-              const float gq = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);                           \
+              const float gq = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);   /* SGN: sc is 0 or 1 */   \
               v[jj][h].c = gq;                                                                 \
               if (LM == 3) {                                                                   \
                 _Pragma("unroll") for (int l = 0; l < NL; ++l)                                 \
@@ -309,24 +319,39 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
             }
           }
         }
-        if (round == 0 && jn > 0) mbar_wait_bounded(&ctl.vfree, (uint32_t)((jn - 1) & 1));
+        const int vb = SGN ? (jn & 1) : 0;
+        unsigned char *vhi = sV + vb * L::VPART, *vlo = sV + L::VPART;
+        if (round == 0 && jn >= NVB)
+          mbar_wait_bounded(&ctl.vfree[vb], (uint32_t)(((jn / NVB) - 1) & 1));
 #pragma unroll
         for (int jj = 0; jj < PJ; ++jj) {
           const int r = q * 32 + 2 * (round * PJ + jj) + (lane >> 4);   // row of the K = 128 px dim
-          uint4 h, l;
-          split_pack2(v[jj][0].x, v[jj][0].y, h.x, l.x);
-          split_pack2(v[jj][0].z, v[jj][0].w, h.y, l.y);
-          split_pack2(v[jj][1].x, v[jj][1].y, h.z, l.z);
-          split_pack2(v[jj][1].z, v[jj][1].w, h.w, l.w);
           const uint32_t off = (uint32_t)(r >> 3) * 1024u +
                                sw128((uint32_t)(r & 7) * 128u + (coff & 127u)) + (coff & ~127u);
-          *reinterpret_cast<uint4 *>(vhi + off) = h;
-          *reinterpret_cast<uint4 *>(vlo + off) = l;
+          uint4 h, l;
+          if constexpr (SGN) {                           // -1 / 0 / +1: exact in bf16, no lo part
+            const __nv_bfloat162 b0 = __floats2bfloat162_rn(v[jj][0].x, v[jj][0].y);
+            const __nv_bfloat162 b1 = __floats2bfloat162_rn(v[jj][0].z, v[jj][0].w);
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[jj][1].x, v[jj][1].y);
+            const __nv_bfloat162 b3 = __floats2bfloat162_rn(v[jj][1].z, v[jj][1].w);
+            h.x = *reinterpret_cast<const uint32_t *>(&b0);
+            h.y = *reinterpret_cast<const uint32_t *>(&b1);
+            h.z = *reinterpret_cast<const uint32_t *>(&b2);
+            h.w = *reinterpret_cast<const uint32_t *>(&b3);
+            *reinterpret_cast<uint4 *>(vhi + off) = h;
+          } else {
+            split_pack2(v[jj][0].x, v[jj][0].y, h.x, l.x);
+            split_pack2(v[jj][0].z, v[jj][0].w, h.y, l.y);
+            split_pack2(v[jj][1].x, v[jj][1].y, h.z, l.z);
+            split_pack2(v[jj][1].z, v[jj][1].w, h.w, l.w);
+            *reinterpret_cast<uint4 *>(vhi + off) = h;
+            *reinterpret_cast<uint4 *>(vlo + off) = l;
+          }
         }
       }
       if (!live) continue;
       fence_async_smem();
-      mbar_arrive_warp(&ctl.vfull);
+      mbar_arrive_warp(&ctl.vfull[SGN ? (jn & 1) : 0]);
       if (warp == 0 && jn < 2) CB_STAMP(3, 0, 1 + jn);
       ++jn;
     }
@@ -360,10 +385,14 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
         {
           uint32_t ra[32], rb[32];
           const uint32_t ta = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
-          tmem_ld_32x32(ta, ra);
-          tmem_ld_32x32(ta + 32, rb);
+          tmem_ld_32x32_nowait(ta, ra);               // both halves in flight, one wait
+          tmem_ld_32x32_nowait(ta + 32, rb);
+          tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
+          for (int k = 0; k < 32; ++k) {
+            acc[k] = __uint_as_float(ra[k]) + __uint_as_float(rb[k]);
+            if (SGN) acc[k] *= l1.scale;
+          }
         }
         tc_fence_before();
         mbar_arrive_warp(&ctl.accfree[buf]);
@@ -424,7 +453,9 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
         if (j < 0) break;
         const CbJob jb = cb_job(j, nblk, tile_w, ch0, nch, offsets, wcount);
         if (jb.nbat <= 0) continue;
-        mbar_wait_bounded(&ctl.vfull, (uint32_t)(jn & 1));
+        constexpr int NVB = SGN ? 2 : 1;
+        const int vb = SGN ? (jn & 1) : 0;
+        mbar_wait_bounded(&ctl.vfull[vb], (uint32_t)((jn / NVB) & 1));
         for (int gi = 0; gi < jb.nbat; ++gi, ++gs) {
           const int st = gs & 1, buf = gs & 1;
           if (gs < 16) CB_STAMP(2, gs, 0);
@@ -435,17 +466,17 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
           if (gs < 16) CB_STAMP(2, gs, 2);
           const uint32_t d = tb + (uint32_t)(buf * 64);
           for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ahi = v_desc0 + (uint64_t)((ks * 2048) >> 4);
+            const uint64_t ahi = v_desc0 + (uint64_t)((vb * L::VPART + ks * 2048) >> 4);
             const uint64_t alo = ahi + (uint64_t)(L::VPART >> 4);
             const uint64_t bw = w_desc0 + (uint64_t)((st * 16384 + ks * 2048) >> 4);
             umma_bf16_ss(d, ahi, bw, idesc, ks > 0 ? 1u : 0u);
-            umma_bf16_ss(d, alo, bw, idesc, 1u);
+            if (!SGN) umma_bf16_ss(d, alo, bw, idesc, 1u);
           }
           umma_commit(&ctl.wfree[st]);
           umma_commit(&ctl.accfull[buf]);
           if (gs < 16) CB_STAMP(2, gs, 3);
         }
-        umma_commit(&ctl.vfree);                     // the v_render block may be overwritten
+        umma_commit(&ctl.vfree[vb]);                 // the v_render block may be overwritten
         ++jn;
       }
     }
@@ -458,7 +489,7 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
   if (warp == 9) tmem_dealloc<L::TCOLS>(tb);
 }
 
-template <int LM>
+template <int LM, bool SGN = false>
 int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const unsigned char *wcache,
               const int *wmeta, const int *wlist, int *wcount, const float *v_render,
               float *v_colors, CbL1 l1, cudaStream_t st) {
@@ -467,7 +498,7 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   const int hh = (H + 7) / 8;
   const int nblk = (nch + 127) / 128;
   {   // per-device attribute: set on every launch (a process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<LM>,
+    cudaError_t e = cudaFuncSetAttribute(blend_bwd_cached<LM, SGN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     if (e != cudaSuccess) return (int)e;
   }
@@ -478,7 +509,7 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
   cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
-  blend_bwd_cached<LM><<<grid, CB_THREADS, L::BYTES, st>>>(
+  blend_bwd_cached<LM, SGN><<<grid, CB_THREADS, L::BYTES, st>>>(
       D, ch0, nch, nblk, W, H, tw, njobs, offsets, wcache, wmeta, wlist, wcount, jobctr, v_render,
       v_colors, l1);
   return (int)cudaGetLastError();
@@ -503,6 +534,15 @@ mark_rows_kernel(int tile_w, int n_half, const int *__restrict__ offsets,
 }
 
 }  // namespace
+
+// 1 (default) = the fused single-level L1 backward without a mask stages sign(render - target)
+// exactly (SGN above); 0 = always the hi / lo split of scale * sign (A/B switch for tests)
+int g_bwd_sign_operand = 1;
+extern "C" int gags_set_bwd_sign_operand(int32_t on) {
+  if (on != 0 && on != 1) return GAGS_EINVAL;
+  g_bwd_sign_operand = on;
+  return 0;
+}
 
 extern "C" int gags_blend_bwd_features_cached(int32_t D, int32_t width, int32_t height,
                                               const int32_t *offsets, const void *wcache,
@@ -546,8 +586,11 @@ extern "C" int gags_blend_bwd_features_cached_l1(int32_t D, int32_t width, int32
   const CbL1 l1{seg, emb, mask, loss_out, n_seg, grad_scale, nullptr, nullptr, 0};
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = launch_cb<1>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
-                                render, v_colors, l1, st);
+    const int rc = (mask == nullptr && g_bwd_sign_operand)
+                       ? launch_cb<1, true>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
+                                            wcount, render, v_colors, l1, st)
+                       : launch_cb<1, false>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
+                                             wcount, render, v_colors, l1, st);
     if (rc != 0) return rc;
   }
   return 0;

@@ -382,6 +382,10 @@ int gags_set_fwd_variant(int32_t variant);
  * tile.  Bit-identical outputs; process-wide.                                                     */
 int gags_set_blend_pass(int32_t persistent);
 
+/* Tuning hook: 1 (default) = gags_blend_bwd_features_cached_l1 without a mask stages the exact sign
+ * operand (one bf16 part, scale applied to the accumulator); 0 = the hi / lo split of scale * sign.  */
+int gags_set_bwd_sign_operand(int32_t on);
+
 /* Zero-fill with a small grid (a quarter of the thread slots), meant to run on a second stream
  * beside latency-bound kernels; ptr 16-B aligned, bytes % 16 == 0.                               */
 int gags_zero_fill(void *ptr, int64_t bytes, void *stream);

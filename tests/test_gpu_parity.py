@@ -683,7 +683,10 @@ def test_fused_l1_backward_equals_loss_then_backward(H, W, D, with_mask, direct)
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 1e-5 * abs(a)
     assert float(g0.abs().max()) > 0
-    assert rel_err(g1, g0) < 2e-6
+    # with a mask both routes stage the hi / lo split of scale * m * sign: same operand, 2e-6.  Without
+    # one the fused kernel stages the sign itself (exact in bf16) and scales the accumulator, while
+    # the two-kernel route still carries the 2^-17 representation error of scale in every term
+    assert rel_err(g1, g0) < (2e-6 if with_mask else 1e-5)
 
 
 def test_fused_l1_backward_falls_back_without_cache():
