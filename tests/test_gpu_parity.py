@@ -1072,3 +1072,43 @@ def test_two_pass_forward_equals_single_pass():
                                          _C.stream_ptr()) != 0
     assert _C.lib.gags_blend_fwd_from_cache(None, 64, None, 4, 4, None, None, None, None, None, None,
                                             None, _C.stream_ptr()) != 0
+
+
+def test_sign_operand_backward_matches_hi_lo_operand():
+    """The fused L1 backward without a mask in its two operand forms — the exact sign (default) and
+    the hi / lo split of scale * sign — on the same cached forward: same loss (up to the order of
+    its atomic partial sums), gradients within 1e-5 of scale (the split form carries the 2^-17
+    representation error of the scale in every term)."""
+    from gags_b200 import _C
+    from gags_b200.arguments import OptimizationParams
+    from gags_b200.gaussian_renderer import render
+    from gags_b200.optim import FusedAdam
+    from gags_b200.scene import GaussianModel
+    from gags_b200.synthetic import make_scene
+    from gags_b200.utils.loss_utils import l1_backward_fused
+    dev = torch.device("cuda:0")
+    H, W, D = 88, 144, 256
+    scene = make_scene(5000, H, W, D, seed=9, n_views=2, sigma_px_median=1.5)
+    g = torch.Generator().manual_seed(2)
+    seg = torch.randint(-1, 6, (H, W), generator=g, dtype=torch.int32).to(dev)
+    emb = (0.2 * torch.randn(6, D, generator=g)).to(dev)
+    bg = torch.zeros(3, device=dev)
+    out = []
+    try:
+        for sign in (1, 0):
+            assert _C.lib.gags_set_bwd_sign_operand(sign) == 0
+            pc = GaussianModel(3, device=dev)
+            pc.create_from_tensors(scene.xyz, scene.scaling, scene.rotation, scene.opacity,
+                                   scene.features_dc, scene.features_rest, scene.semantic_feature)
+            pc.training_setup(OptimizationParams(), fused_optimizer=True)
+            pc.optimizer = FusedAdam([pc._semantic_feature], lr=1e-3)       # plain .grad handling
+            pkg = render(scene.cameras[0].to(dev), pc, None, bg)
+            loss = l1_backward_fused(pkg["render"], seg, emb)
+            torch.cuda.synchronize()
+            out.append((float(loss), pc._semantic_feature.grad.clone()))
+    finally:
+        _C.lib.gags_set_bwd_sign_operand(1)
+    (l1, g1), (l0, g0) = out
+    assert abs(l1 - l0) <= 1e-6 * abs(l0) and float(g1.abs().max()) > 0
+    assert rel_err(g1, g0) < 1e-5
+    assert _C.lib.gags_set_bwd_sign_operand(2) != 0
