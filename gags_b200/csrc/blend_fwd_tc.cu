@@ -28,6 +28,17 @@
 // Epilogue (warps 0-11): tcgen05.ld (lane = channel, column = pixel) -> + T*background (skipped
 // for an all-zero background) -> 128-B warp-wide streaming stores of the channel-last raster.
 //
+// (The role list above is the round-1 layout, `gags_set_fwd_variant(2)`; the default V3 layout splits
+// the pixel work into front warps 4-7 = scanner + alpha evaluation with lane = Gaussian and chain
+// warps 0-3 = transmittance chain with lane = pixel, and its epilogue issues TMA tensor stores.)
+//
+// Kernels in this file:
+//   blend_fwd_tc<NATOM, V3, 0>   the whole forward in one pass (inference; training without a lazily
+//                                updated feature table), one CTA per half tile, 2 CTAs / SM
+//   blend_fwd_tc<0, true, 1>     weights pass: geometry only, writes alphas + cached weight tiles
+//   blend_fwd_tc<NATOM, true, 2> blend pass from the cache, one CTA per half tile (A/B form)
+//   blend_fwd_pers<NATOM>        blend pass from the cache, ONE persistent CTA per SM (default)
+//
 // Roofline: HBM.  Algorithmic bytes per launch: N_contrib*4D (feature rows, once; re-reads are L2
 // hits) + H*W*(4D+8) (render, alpha, last_ids) + 12 B per list entry scanned.
 #include <cuda.h>
