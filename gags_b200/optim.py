@@ -277,6 +277,11 @@ class FusedAdam(torch.optim.Optimizer):
                                 lz.apply(p.grad, rows[1].flags, t, lr)
                                 done = torch.cuda.Event()
                                 done.record(us)
+                            # should the caller drop `.grad` (or this optimiser) right away, the
+                            # allocator must not recycle these blocks under the running step
+                            for tns in (p.grad, rows[1].flags, lz.last, lz.consts, st["exp_avg"],
+                                        st["exp_avg_sq"]):
+                                tns.record_stream(us)
                             lz.pending = done
                             R.param_ready_events[p.data_ptr()] = done
                             R.sink_ready_events[p.grad.data_ptr()] = done
