@@ -601,6 +601,8 @@ def main():
                "tile_ms_p10_p50_p90": info["tile_ms_p10_p50_p90"],
                "wall_s": round(time.time() - t0, 1)}
         stats["n_isects"] = info["n_isects"]
+        for key in ("gauss_per_tile_mean", "gauss_per_tile_max", "k_eff_sampled"):
+            stats[key] = info[key]
 
     if rank == 0:
         line = {"metric": METRICS[cfg], "value": value, "unit": "views/s", "n_gpus": world,

@@ -35,8 +35,7 @@ def time_view(scene, cam, D: int, n_tiles: int = 256, seed: int = 0, threads: in
     sample = torch.randperm(tw * th, generator=g)[:n_tiles].tolist()
     feats = scene.semantic_feature[:, :D]
     op = opac.squeeze(-1)
-    t1 = time.perf_counter()
-    per_tile = []
+    per_tile, keff = [], []
     for t in sample:
         tt = time.perf_counter()
         s, e = o2[t], o2[t + 1]
@@ -55,7 +54,8 @@ def time_view(scene, cam, D: int, n_tiles: int = 256, seed: int = 0, threads: in
             v_out = torch.sign(out)                   # dL1/dout
             _ = w.T @ v_out                           # feature backward
         per_tile.append((time.perf_counter() - tt) * 1e3)
-    t_blend = (time.perf_counter() - t1) * (tw * th) / max(1, len(sample))
+        keff.append(float((w > 0).sum(dim=1).float().mean()))      # (outside the timed part)
+    t_blend = sum(per_tile) * 1e-3 * (tw * th) / max(1, len(sample))
     pt = sorted(per_tile) or [0.0]
     spread = [round(pt[int(q * (len(pt) - 1))], 3) for q in (0.1, 0.5, 0.9)]
     total = t_geom + t_blend
@@ -64,4 +64,8 @@ def time_view(scene, cam, D: int, n_tiles: int = 256, seed: int = 0, threads: in
                 sample=f"projection+keys+sort on all N={scene.xyz.shape[0]}; blend "
                        f"{'fwd+bwd_feat' if backward else 'fwd'} on {len(sample)} of {tw * th} "
                        "tiles, extrapolated",
-                n_isects=int(keys.numel()), n_visible=int((radii > 0).sum()))
+                n_isects=int(keys.numel()), n_visible=int((radii > 0).sum()),
+                # workload descriptors every result row carries
+                gauss_per_tile_mean=round(keys.numel() / float(tw * th), 1),
+                gauss_per_tile_max=int(max(o2[i + 1] - o2[i] for i in range(tw * th))),
+                k_eff_sampled=round(sum(keff) / max(1, len(keff)), 1))
