@@ -25,6 +25,7 @@
 //
 // Roofline: HBM — H*W*4D (v_render, once) + 16.1 KB per cached batch + N_contrib*4D*2 (reduction
 // target; the reductions resolve in L2).
+#include <cstdlib>
 #include "blend_tc_common.cuh"
 
 #ifdef GAGS_TC_TIMING
@@ -504,7 +505,12 @@ int launch_cb(int D, int ch0, int nch, int W, int H, const int *offsets, const u
   }
   const long long njobs = (long long)tw * nblk * hh;
   if (njobs > 0x7fffffffLL - 4096) return GAGS_ERANGE;
-  const long long want = 2LL * gags_sm_count();                  // two persistent CTAs per SM
+  static int ctas_per_sm = 0;                                    // tuning: GAGS_B200_BWD_CTAS=1|2
+  if (ctas_per_sm == 0) {
+    const char *e = getenv("GAGS_B200_BWD_CTAS");
+    ctas_per_sm = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  const long long want = (long long)ctas_per_sm * gags_sm_count();   // persistent CTAs (two per SM)
   const unsigned grid = (unsigned)(njobs < want ? njobs : want);
   int *jobctr = wcount + (size_t)tw * hh;            // the caller's extra int behind the counts
   cudaError_t e = cudaMemsetAsync(jobctr, 0, sizeof(int), st);
