@@ -302,7 +302,8 @@ blend_bwd_cached(int D, int ch0, int nch, int nblk, int W, int H, int tile_w, lo
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) vs[l] += __shfl_xor_sync(0xffffffffu, vs[l], o);
                 if ((lane & 15) == 0 && mk[jj] != 0.f && xx < W && yy < H)
-                  atomicAdd(l1.v_scale + (size_t)l * l1.hw + (size_t)yy * W + xx, vs[l]);
+                  atomicAdd(l1.v_scale + (size_t)l * l1.hw + (size_t)yy * W + xx,
+                            SGN ? vs[l] * l1.scale : vs[l]);     // SGN: gq above is the bare sign
               }
             }
           }
@@ -627,8 +628,12 @@ extern "C" int gags_blend_bwd_features_cached_sam(int32_t D, int32_t width, int3
                 (long long)width * height};
   for (int ch0 = 0; ch0 < D; ch0 += 256) {
     const int nch = (D - ch0) < 256 ? (D - ch0) : 256;
-    const int rc = launch_cb<3>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist, wcount,
-                                render, v_colors, l1, st);
+    // the three-level target never has a pixel mask: the sign operand applies (see SGN)
+    const int rc = g_bwd_sign_operand
+                       ? launch_cb<3, true>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
+                                            wcount, render, v_colors, l1, st)
+                       : launch_cb<3, false>(D, ch0, nch, width, height, offsets, wc, wmeta, wlist,
+                                             wcount, render, v_colors, l1, st);
     if (rc != 0) return rc;
   }
   return 0;

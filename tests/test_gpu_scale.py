@@ -498,7 +498,9 @@ def test_fused_sam_backward_equals_loss_then_backward(D, want_vs):
         res.append((float(loss), pc._semantic_feature.grad.clone(), vs))
     (l0, g0, v0), (l1, g1, v1) = res
     assert abs(l0 - l1) < 1e-5 * abs(l0)
-    assert float(g0.abs().max()) > 0 and rel_err(g1, g0) < 2e-6
+    # the fused kernel stages the exact sign and scales the accumulator; the two-kernel route carries
+    # the 2^-17 representation error of the scale's hi / lo split in every term
+    assert float(g0.abs().max()) > 0 and rel_err(g1, g0) < 1e-5
     if want_vs:
         assert rel_err(v1, v0) < 1e-5
     else:
