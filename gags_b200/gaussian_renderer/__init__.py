@@ -47,7 +47,8 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, feature_mode=True
         flags, smod = 0, 1.0
 
     if feature_mode:
-        colors = pc.get_semantic_feature                       # [N, D]
+        raw = getattr(pc, "_semantic_feature_for_render", None)
+        colors = raw() if raw is not None else pc.get_semantic_feature   # [N, D]
         sh_degree = None
         bg_color = bg_color[0].repeat(colors.shape[-1])
     elif override_color is not None:

@@ -109,6 +109,13 @@ class GaussianModel:
 
     @property
     def get_semantic_feature(self):
+        # a lazily-updated table (FusedAdam(lazy_rows)) is materialised for whoever reads it through
+        # the reference's getter; render() takes it through _semantic_feature_for_render() instead and
+        # brings only the rows the view reads up to date
+        self._flush_lazy()
+        return self._semantic_feature
+
+    def _semantic_feature_for_render(self):
         return self._semantic_feature
 
     def rewrite_semantic_feature(self, x):

@@ -1005,6 +1005,9 @@ def test_lazy_training_renders_and_updates_like_dense_training(D, views_per_step
             behind_seen = behind_seen or not torch.equal(p.detach(), ps.detach())
             assert int((lz.last < it).sum()) > 0
     assert behind_seen                                     # the lazy route was really taken
+    # the reference's getter hands out the materialised table (it flushes), no explicit flush needed
+    if views_per_step == 1:
+        assert torch.equal(pc.get_semantic_feature.detach(), ps.detach())
     # an evaluation render flushes by itself and sees the dense parameters
     with torch.no_grad():
         cam = scene.cameras[5].to(dev)
