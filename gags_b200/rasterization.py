@@ -7,7 +7,9 @@ Every stage is a hand-written sm_100a kernel reached through the C-ABI of includ
     _Project   K1 (+K2 bwd)   means/quats/scales/opacities -> radii, means2d, depths, conics, opac
     _SHColors  K3 (+bwd)      SH coefficients -> RGB
     binning    K4-K6          tile count (fused in K1) -> scan -> emit -> radix sort -> offsets
-    _Blend     K7 (+K8 bwd)   one launch for any D; feature-only backward when geometry is frozen
+    _Blend     K7 (+K8 bwd)   one launch for any D; feature-only backward when geometry is frozen;
+                              with a lazily updated feature table (optim.LazyRows) the forward runs
+                              as weights pass -> flag + catch up the rows it reads -> blend pass
 
 There is no CPU path: CPU tensors raise.
 """
