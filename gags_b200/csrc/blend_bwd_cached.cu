@@ -15,13 +15,16 @@
 // k-step  Vhi x [Whi|Wlo]  and  Vlo x [Whi|Wlo]  (N = 64 each), column g + column 32+g =
 // (Vhi+Vlo)(Whi+Wlo).  One CTA = half tile x 128 channels with a 64 KB A tile, so TWO CTAs share an
 // SM and one's v_render staging (pure HBM latency) hides behind the other's MMAs and reductions.
-// Accumulators are double-buffered in TMEM; the epilogue warps drain a step (tcgen05.ld -> add halves -> [32 g][128 ch] fp32
-// tile in smem -> ONE bulk async reduction per Gaussian row, cp.reduce.async.bulk .add.f32, 512 B
-// contiguous: the adds happen at L2 and the SM's LSU issues 32 instructions per tile instead of
-// 256 vector reds, which measured ~130 cycles each per SM) while the next step's MMAs run.
+// Accumulators are double-buffered in TMEM; the epilogue warps drain a step (two tcgen05.ld in flight
+// -> add halves -> per-warp transpose through 4 KB of shared memory -> 16-byte vector reductions,
+// red.global.add.v4.f32, 128 contiguous bytes per Gaussian row and warp; exactly-zero rows are
+// skipped) while the next step's MMAs run.  (Shared-memory staged bulk async reductions were tried
+// first and were limited by the staging they pin; both forms meet the same L2 ceiling.)
+// With the fused L1 loss and no pixel mask the staged operand is the exact SIGN (one bf16 part, see
+// SGN below): half the MMAs and staging stores, and the operand buffer is double-buffered.
 //
 // Warps: 0-3 v_render staging, 4-7 epilogue (the four TMEM lane quarters), 8 bulk-copy producer,
-// 9 MMA issue.  Persistent, two CTAs per SM.
+// 9 MMA issue.  Persistent, two CTAs per SM (one is 40 % slower, a second epilogue set 2x slower).
 //
 // Roofline: HBM — H*W*4D (v_render, once) + 16.1 KB per cached batch + N_contrib*4D*2 (reduction
 // target; the reductions resolve in L2).
